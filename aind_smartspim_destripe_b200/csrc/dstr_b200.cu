@@ -1,0 +1,956 @@
+// libdstr_b200.so - host side of the B200-native destripe engine: C-ABI (include/dstr_b200.h),
+// workspace management, kernel orchestration and the H2D / compute / D2H stream pipeline that
+// replaces the reference's multiprocessing producer/consumer
+// (/root/reference/code/aind_smartspim_destripe/zarr_destriper.py:797-906).
+#include "dstr_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dstr_b200.h"
+
+using namespace dstr;
+
+namespace {
+
+constexpr int kMaxLevels = 16;
+constexpr int kFilterTaps = 6;  // db3
+
+std::mutex g_err_mutex;
+std::string g_last_error;
+
+void set_global_error(const std::string& s) {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = s;
+}
+
+int max_level_1d(int n) {
+    // pywt.dwt_max_level: floor(log2(n / (F - 1)))
+    if (n < kFilterTaps - 1) return 0;
+    int lvl = 0;
+    while ((long long)(kFilterTaps - 1) << (lvl + 1) <= (long long)n) ++lvl;
+    return lvl;
+}
+
+struct LevelGeom {
+    int H, W, pitch;
+    size_t pstride;  // floats per plane
+};
+
+struct TapTable {
+    float sigma[2] = {-1.f, -1.f};  // [cells, no_cells] the table was built for
+    int ntap_pad = 0, u_lo = 0;
+    float* d_taps = nullptr;  // [2 cfg][2][ntap_pad]
+};
+
+struct TimerSpan {
+    int id;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct dstr_ctx {
+    int device = 0;
+    int zcap = 0;
+    int H = 0, W = 0;
+    int Lmax = 0;
+    LevelGeom geom[kMaxLevels + 1];
+    float* d_A[kMaxLevels + 1] = {};
+    float* d_H[kMaxLevels + 1] = {};
+    LevelStat* d_lstat = nullptr;  // [Lmax][zcap]
+    PlaneStat* d_pstat = nullptr;  // [zcap]
+    TapTable taps[kMaxLevels + 1];
+    float* d_flat = nullptr;
+    float* d_dark = nullptr;
+    bool have_flat_dark = false;
+    // staging for host buffers (double buffered)
+    void* d_in[2] = {nullptr, nullptr};
+    void* d_out[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    int subchunk = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    float fg_half_thr = 384.f;
+    // instrumentation
+    bool profiling = false;
+    int debug_stop = DSTR_STAGE_NONE;
+    int last_levels = 0;
+    int last_z = 0;
+    double timers[DSTR_NUM_TIMERS] = {};
+    uint64_t launches = 0;
+    std::vector<TimerSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    std::string err;
+};
+
+namespace {
+
+int fail(dstr_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    set_global_error(msg);
+    return code;
+}
+
+#define CK(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            return fail(ctx, (int)e_,                                                         \
+                        std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                            ":" + std::to_string(__LINE__) + ")");                            \
+        }                                                                                     \
+    } while (0)
+
+// ---- float16 foreground rule (filtering.py:78-81) -----------------------------------------------
+// mask = sigmoid((float16(v) - 400) / 20) > 0.3 evaluated in float16.  The rule is monotone in
+// float16(v); the smallest float16 that satisfies it is found by emulating the float16
+// arithmetic with correctly rounded conversions (exp evaluated in float32 then rounded, as
+// numpy does for float16 ufuncs).
+float half_round(float x) { return __half2float(__float2half_rn(x)); }
+
+float half_from_bits(unsigned bits) {
+    __half_raw hr;
+    hr.x = (unsigned short)bits;
+    return __half2float(__half(hr));
+}
+
+bool fg_rule(float h, float thr) {
+    float zf = half_round(h - 400.0f);
+    zf = half_round(zf / 20.0f);
+    const float e = half_round(expf(-zf));
+    const float den = half_round(1.0f + e);
+    const float f = half_round(1.0f / den);
+    return f > thr;
+}
+
+// smallest float16 value (ascending over all finite float16) for which the rule holds;
+// -inf if it holds everywhere, +inf if nowhere
+float find_fg_half_threshold(float threshold_mask) {
+    const float thr = half_round(threshold_mask);
+    // negatives, ascending: bit patterns 0xfbff (-65504) down to 0x8000 (-0)
+    for (unsigned bits = 0xfbffu; bits >= 0x8000u; --bits) {
+        if (fg_rule(half_from_bits(bits), thr)) return bits == 0xfbffu ? -INFINITY : half_from_bits(bits);
+    }
+    for (unsigned bits = 0; bits <= 0x7bffu; ++bits) {
+        if (fg_rule(half_from_bits(bits), thr)) return half_from_bits(bits);
+    }
+    return INFINITY;
+}
+
+// ---- time-domain form of the packed-rfft notch (filtering.py:206-215, scipy.fftpack layout) --
+// Y_pk[k] = w[k] X_pk[k], w[k] = exp(-k^2 / (2 s^2)) on the packed index k:
+//   Re X_j gets a_j = w[2j-1], Im X_j gets b_j = w[2j], DC gets w[0], Nyquist (n even) w[n-1].
+//   p_j = (a_j + b_j)/2 multiplies X_j, q_j = (a_j - b_j)/2 multiplies conj(X_j).
+void notch_kernels_host(int n, double s, std::vector<double>& hp, std::vector<double>& hq) {
+    hp.assign(n, 0.0);
+    hq.assign(n, 0.0);
+    auto w = [&](int k) { return std::exp(-((double)k * (double)k) / (2.0 * s * s)); };
+    const int nh = n / 2;
+    const int J = (n % 2 == 0) ? nh + 1 : (n + 1) / 2;
+    std::vector<double> p(J), q(J), wt(J);
+    p[0] = w(0);
+    q[0] = 0.0;
+    wt[0] = 1.0;
+    for (int j = 1; j < J; ++j) {
+        if (n % 2 == 0 && j == nh) {
+            p[j] = w(n - 1);
+            q[j] = 0.0;
+            wt[j] = 1.0;
+        } else {
+            const double a = w(2 * j - 1), b = w(2 * j);
+            p[j] = 0.5 * (a + b);
+            q[j] = 0.5 * (a - b);
+            wt[j] = 2.0;
+        }
+    }
+    // cos(2 pi j u / n) via a table indexed by (j*u) mod n
+    std::vector<double> ct(n);
+    for (int i = 0; i < n; ++i) ct[i] = std::cos(2.0 * M_PI * (double)i / (double)n);
+    for (int u = 0; u < n; ++u) {
+        double sp = 0.0, sq = 0.0;
+        long long idx = 0;
+        for (int j = 0; j < J; ++j) {
+            const double c = ct[idx];
+            sp += wt[j] * p[j] * c;
+            sq += wt[j] * q[j] * c;
+            idx += u;
+            if (idx >= n) idx -= n;
+        }
+        hp[u] = sp / n;
+        hq[u] = sq / n;
+    }
+}
+
+int build_taps(dstr_ctx* ctx, int level, float sigma_cells, float sigma_nocells) {
+    TapTable& T = ctx->taps[level];
+    if (T.d_taps && T.sigma[0] == sigma_cells && T.sigma[1] == sigma_nocells) return 0;
+    const int n = ctx->geom[level].W;
+    const int Hl = ctx->geom[level].H;
+    const int ntap = n;  // full circular support (exact)
+    const int ntap_pad = (ntap + 7) & ~7;
+    const int u_lo = -(n / 2);
+    std::vector<float> host((size_t)4 * ntap_pad, 0.f);
+    const float sig[2] = {sigma_nocells, sigma_cells};  // cfg 0 = no_cells, cfg 1 = cells
+    for (int cfg = 0; cfg < 2; ++cfg) {
+        if (!(sig[cfg] > 0.f)) continue;  // unused configuration
+        // s = rows of this band * sigma / min(H, W)   (filtering.py:180,208-213)
+        const double wf = (double)sig[cfg] / (double)std::min(ctx->H, ctx->W);
+        const double s = (double)Hl * wf;
+        std::vector<double> hp, hq;
+        notch_kernels_host(n, s, hp, hq);
+        float* tp = host.data() + (size_t)cfg * 2 * ntap_pad;
+        float* tq = tp + ntap_pad;
+        for (int k = 0; k < ntap; ++k) {
+            int u = u_lo + k;
+            int m = ((u % n) + n) % n;
+            tp[k] = (float)hp[m];
+            tq[k] = (float)hq[m];
+        }
+    }
+    if (!T.d_taps || T.ntap_pad != ntap_pad) {
+        if (T.d_taps) cudaFree(T.d_taps);
+        T.d_taps = nullptr;
+        CK(ctx, cudaMalloc(&T.d_taps, host.size() * sizeof(float)));
+    }
+    CK(ctx, cudaMemcpyAsync(T.d_taps, host.data(), host.size() * sizeof(float),
+                            cudaMemcpyHostToDevice, ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    T.ntap_pad = ntap_pad;
+    T.u_lo = u_lo;
+    T.sigma[0] = sigma_cells;
+    T.sigma[1] = sigma_nocells;
+    return 0;
+}
+
+cudaEvent_t get_event(dstr_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedTimer {
+    dstr_ctx* ctx;
+    int id;
+    cudaEvent_t a = nullptr;
+    ScopedTimer(dstr_ctx* c, int i) : ctx(c), id(i) {
+        if (ctx->profiling) {
+            a = get_event(ctx);
+            cudaEventRecord(a, ctx->s_comp);
+        }
+    }
+    ~ScopedTimer() {
+        if (ctx->profiling) {
+            cudaEvent_t b = get_event(ctx);
+            cudaEventRecord(b, ctx->s_comp);
+            ctx->spans.push_back({id, a, b});
+        }
+    }
+};
+
+void resolve_timers(dstr_ctx* ctx) {
+    for (auto& sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ctx->timers[sp.id] += ms;
+        ctx->ev_pool.push_back(sp.a);
+        ctx->ev_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+}
+
+template <int EPL>
+int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem,
+                  const DispatchParams& dp) {
+    CK(ctx, cudaFuncSetAttribute(filter_rows_kernel<EPL>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((fa.Hl + FR_ROWS - 1) / FR_ROWS, Z);
+    filter_rows_kernel<EPL><<<grid, FR_THREADS, smem, ctx->s_comp>>>(fa, ctx->d_pstat, dp);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Process z planes resident on the device (d_in -> d_out) on the compute stream.
+int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, int out_dtype, int z,
+                   const dstr_params& cells, const dstr_params& no_cells, float high_int, int mode,
+                   int flags, int L) {
+    cudaStream_t st = ctx->s_comp;
+    const int H = ctx->H, W = ctx->W;
+    const bool stack = (flags & DSTR_FLAG_STACK_OTSU) != 0;
+    const int stat_stride = stack ? 0 : 1;
+    const size_t level_stride = (size_t)ctx->zcap;
+    ctx->last_levels = L;
+    ctx->last_z = z;
+
+    DispatchParams dp;
+    dp.max_thr_cells = cells.max_threshold;
+    dp.max_thr_nocells = no_cells.max_threshold;
+    dp.high_int = high_int;
+    dp.mode = (mode == DSTR_MODE_DISPATCH) ? 1 : 0;
+
+    ScopedTimer t_all(ctx, 7);
+    if (L > 0) {
+        CK(ctx, cudaMemsetAsync(ctx->d_lstat, 0, sizeof(LevelStat) * level_stride * ctx->Lmax, st));
+    }
+    CK(ctx, cudaMemsetAsync(ctx->d_pstat, 0, sizeof(PlaneStat) * ctx->zcap, st));
+
+    if (L == 0 && dp.mode == 1) {
+        // dispatch is irrelevant with zero levels (both configs give x + 2)
+    }
+
+    // ---- analysis -----------------------------------------------------------------------------
+    for (int l = 1; l <= L; ++l) {
+        ScopedTimer t(ctx, l == 1 ? 0 : 1);
+        const LevelGeom& gs = ctx->geom[l - 1];
+        const LevelGeom& go = ctx->geom[l];
+        dim3 grid((go.W + AN_TOX - 1) / AN_TOX, (go.H + AN_TOY - 1) / AN_TOY, z);
+        LevelStat* ls = ctx->d_lstat + (size_t)(l - 1) * level_stride;
+        if (l == 1) {
+            if (in_dtype == DSTR_U16) {
+                analysis_kernel<uint16_t, true><<<grid, AN_THREADS, 0, st>>>(
+                    (const uint16_t*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H,
+                    go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+            } else {
+                analysis_kernel<float, true><<<grid, AN_THREADS, 0, st>>>(
+                    (const float*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W,
+                    go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+            }
+        } else {
+            analysis_kernel<float, false><<<grid, AN_THREADS, 0, st>>>(
+                ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H,
+                go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+        }
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (ctx->debug_stop == DSTR_STAGE_ANALYSIS) return 0;
+
+    if (L > 0) {
+        // ---- histogram + Otsu ------------------------------------------------------------------
+        {
+            ScopedTimer t(ctx, 2);
+            for (int l = 1; l <= L; ++l) {
+                const LevelGeom& g = ctx->geom[l];
+                const int nblk = std::max(1, std::min(g.H, (g.H * g.W + 8191) / 8192));
+                dim3 grid(nblk, z);
+                hist_kernel<<<grid, 256, 0, st>>>(ctx->d_H[l], g.H, g.W, g.pitch, g.pstride,
+                                                  ctx->d_lstat + (size_t)(l - 1) * level_stride,
+                                                  stat_stride);
+                ctx->launches++;
+                CK(ctx, cudaGetLastError());
+            }
+        }
+        {
+            ScopedTimer t(ctx, 3);
+            dim3 grid(stack ? 1 : z, L);
+            otsu_kernel<<<grid, 32, 0, st>>>(ctx->d_lstat, level_stride, stat_stride, ctx->d_pstat,
+                                             dp);
+            ctx->launches++;
+            CK(ctx, cudaGetLastError());
+        }
+        if (ctx->debug_stop == DSTR_STAGE_OTSU) return 0;
+
+        // ---- row filter ------------------------------------------------------------------------
+        {
+            ScopedTimer t(ctx, 4);
+            for (int l = 1; l <= L; ++l) {
+                const LevelGeom& g = ctx->geom[l];
+                const TapTable& T = ctx->taps[l];
+                FilterLevelArgs fa;
+                fa.cH = ctx->d_H[l];
+                fa.Hl = g.H;
+                fa.Wl = g.W;
+                fa.pitch = g.pitch;
+                fa.pstride = g.pstride;
+                fa.lstat = ctx->d_lstat + (size_t)(l - 1) * level_stride;
+                fa.stat_stride = stat_stride;
+                fa.taps = T.d_taps;
+                fa.ntap_pad = T.ntap_pad;
+                fa.u_lo = T.u_lo;
+                fa.n_pad8 = (g.W + 7) & ~7;
+                const int xlen_log = fa.n_pad8 + fa.ntap_pad;
+                fa.xlen_phys = xlen_log / 8 * 9;
+                const size_t smem = sizeof(float) * ((size_t)2 * fa.ntap_pad +
+                                                     (size_t)2 * FR_ROWS * fa.xlen_phys +
+                                                     (size_t)FR_ROWS * fa.n_pad8) +
+                                    (size_t)FR_ROWS * fa.n_pad8;
+                if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
+                const int epl = (g.W + 31) / 32;
+                int rc;
+                if (epl <= 2) rc = launch_filter<2>(ctx, fa, z, smem, dp);
+                else if (epl <= 5) rc = launch_filter<5>(ctx, fa, z, smem, dp);
+                else if (epl <= 9) rc = launch_filter<9>(ctx, fa, z, smem, dp);
+                else if (epl <= 17) rc = launch_filter<17>(ctx, fa, z, smem, dp);
+                else if (epl <= 33) rc = launch_filter<33>(ctx, fa, z, smem, dp);
+                else if (epl <= 65) rc = launch_filter<65>(ctx, fa, z, smem, dp);
+                else return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
+                if (rc) return rc;
+            }
+        }
+        if (ctx->debug_stop == DSTR_STAGE_FILTER) return 0;
+
+        // ---- synthesis of the deltas, levels L..2 ----------------------------------------------
+        {
+            ScopedTimer t(ctx, 5);
+            EpilogueArgs ep0 = {};
+            for (int l = L; l >= 2; --l) {
+                const LevelGeom& g = ctx->geom[l];
+                const LevelGeom& go = ctx->geom[l - 1];
+                dim3 grid((go.W + SY_TX - 1) / SY_TX, (go.H + SY_TY - 1) / SY_TY, z);
+                const float* dA = (l == L) ? nullptr : ctx->d_A[l];
+                synth_kernel<false, float, float><<<grid, SY_THREADS, 0, st>>>(
+                    dA, ctx->d_H[l], g.H, g.W, g.pitch, g.pstride, ctx->d_A[l - 1], go.H, go.W,
+                    go.pitch, go.pstride, nullptr, nullptr, 0, ep0);
+                ctx->launches++;
+                CK(ctx, cudaGetLastError());
+            }
+        }
+        if (ctx->debug_stop == DSTR_STAGE_SYNTH) return 0;
+    }
+
+    // ---- final level + inverse log + epilogue ------------------------------------------------------
+    {
+        ScopedTimer t(ctx, 6);
+        EpilogueArgs ep;
+        ep.flat = ctx->d_flat;
+        ep.dark = ctx->d_dark;
+        ep.shadow = (flags & DSTR_FLAG_SHADOW) ? 1 : 0;
+        ep.expm1 = (flags & DSTR_FLAG_EXPM1) ? 1 : 0;
+        const LevelGeom& g = ctx->geom[L > 0 ? 1 : 0];
+        const float* dA = (L >= 2) ? ctx->d_A[1] : nullptr;
+        const float* dH = (L >= 1) ? ctx->d_H[1] : nullptr;
+        dim3 grid((W + SY_TX - 1) / SY_TX, (H + SY_TY - 1) / SY_TY, z);
+        const size_t ps = (size_t)H * W;
+#define LAUNCH_FINAL(IN_T, OUT_T)                                                                   \
+    synth_kernel<true, IN_T, OUT_T><<<grid, SY_THREADS, 0, st>>>(                                   \
+        dA, dH, g.H, g.W, g.pitch, g.pstride, nullptr, H, W, W, ps, (const IN_T*)d_in, (OUT_T*)d_out, \
+        ps, ep)
+        if (in_dtype == DSTR_U16 && out_dtype == DSTR_U16) LAUNCH_FINAL(uint16_t, uint16_t);
+        else if (in_dtype == DSTR_U16 && out_dtype == DSTR_F32) LAUNCH_FINAL(uint16_t, float);
+        else if (in_dtype == DSTR_F32 && out_dtype == DSTR_U16) LAUNCH_FINAL(float, uint16_t);
+        else LAUNCH_FINAL(float, float);
+#undef LAUNCH_FINAL
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
+size_t dtype_size(int dt) { return dt == DSTR_U16 ? 2 : 4; }
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int ensure_stage(dstr_ctx* ctx, int planes) {
+    const size_t need = (size_t)planes * ctx->H * ctx->W * 4;
+    if (ctx->stage_bytes >= need) return 0;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+        if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+        ctx->d_in[i] = ctx->d_out[i] = nullptr;
+    }
+    ctx->stage_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+        CK(ctx, cudaMalloc(&ctx->d_in[i], need));
+        CK(ctx, cudaMalloc(&ctx->d_out[i], need));
+    }
+    ctx->stage_bytes = need;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* dstr_last_error(const dstr_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_last_error;
+    return copy.c_str();
+}
+
+int dstr_max_level(int H, int W) {
+    if (H <= 0 || W <= 0) return DSTR_E_ARG;
+    return std::min(max_level_1d(H), max_level_1d(W));
+}
+
+int dstr_level_shape(int H, int W, int level, int* H_l, int* W_l) {
+    if (H <= 0 || W <= 0 || level < 0 || !H_l || !W_l) return DSTR_E_ARG;
+    int h = H, w = W;
+    for (int l = 0; l < level; ++l) {
+        h = (h + kFilterTaps - 1) / 2;
+        w = (w + kFilterTaps - 1) / 2;
+    }
+    *H_l = h;
+    *W_l = w;
+    return 0;
+}
+
+float dstr_foreground_threshold(float threshold_mask) { return find_fg_half_threshold(threshold_mask); }
+
+int dstr_notch_kernels(int n, double s, double* hp, double* hq) {
+    if (n <= 0 || !(s > 0.0) || !hp || !hq) return DSTR_E_ARG;
+    std::vector<double> a, b;
+    notch_kernels_host(n, s, a, b);
+    std::memcpy(hp, a.data(), sizeof(double) * n);
+    std::memcpy(hq, b.data(), sizeof(double) * n);
+    return 0;
+}
+
+int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
+    if (!out || max_planes <= 0 || H <= 0 || W <= 0) return fail(nullptr, DSTR_E_ARG, "dstr_create: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice,
+                    std::string("dstr_create: no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, DSTR_E_ARG, "dstr_create: bad device index");
+    dstr_ctx* ctx = new dstr_ctx();
+    ctx->device = device;
+    ctx->zcap = max_planes;
+    ctx->H = H;
+    ctx->W = W;
+    ctx->Lmax = std::min(std::min(max_level_1d(H), max_level_1d(W)), kMaxLevels);
+    *out = nullptr;
+#define CKC(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            int rc_ = fail(nullptr, (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            dstr_destroy(ctx);                                                            \
+            return rc_;                                                                   \
+        }                                                                                 \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    ctx->geom[0] = {H, W, W, (size_t)H * W};
+    for (int l = 1; l <= ctx->Lmax; ++l) {
+        LevelGeom g;
+        g.H = (ctx->geom[l - 1].H + kFilterTaps - 1) / 2;
+        g.W = (ctx->geom[l - 1].W + kFilterTaps - 1) / 2;
+        g.pitch = (g.W + 3) & ~3;
+        g.pstride = (size_t)g.H * g.pitch;
+        ctx->geom[l] = g;
+        CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * g.pstride * max_planes));
+        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * g.pstride * max_planes));
+    }
+    if (ctx->Lmax > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lmax * max_planes));
+    CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));
+    CKC(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CKC(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    }
+#undef CKC
+    ctx->fg_half_thr = find_fg_half_threshold(0.3f);
+    ctx->subchunk = 0;
+    *out = ctx;
+    return 0;
+}
+
+int dstr_destroy(dstr_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->s_comp) cudaStreamSynchronize(ctx->s_comp);
+    if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        if (ctx->d_A[l]) cudaFree(ctx->d_A[l]);
+        if (ctx->d_H[l]) cudaFree(ctx->d_H[l]);
+        if (ctx->taps[l].d_taps) cudaFree(ctx->taps[l].d_taps);
+    }
+    if (ctx->d_lstat) cudaFree(ctx->d_lstat);
+    if (ctx->d_pstat) cudaFree(ctx->d_pstat);
+    if (ctx->d_flat) cudaFree(ctx->d_flat);
+    if (ctx->d_dark) cudaFree(ctx->d_dark);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+        if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    for (auto& sp : ctx->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+    return 0;
+}
+
+int dstr_set_flat_dark(dstr_ctx* ctx, const float* flat, const float* dark) {
+    if (!ctx) return DSTR_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!flat || !dark) {
+        ctx->have_flat_dark = false;
+        return 0;
+    }
+    const size_t bytes = sizeof(float) * (size_t)ctx->H * ctx->W;
+    if (!ctx->d_flat) CK(ctx, cudaMalloc(&ctx->d_flat, bytes));
+    if (!ctx->d_dark) CK(ctx, cudaMalloc(&ctx->d_dark, bytes));
+    CK(ctx, cudaMemcpyAsync(ctx->d_flat, flat, bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+    CK(ctx, cudaMemcpyAsync(ctx->d_dark, dark, bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    ctx->have_flat_dark = true;
+    return 0;
+}
+
+int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, int out_dtype, int Z,
+                      const dstr_params* cells, const dstr_params* no_cells, float high_int,
+                      int mode, int flags) {
+    if (!ctx) return DSTR_E_ARG;
+    if (!in || !out || Z <= 0 || !no_cells) return fail(ctx, DSTR_E_ARG, "dstr_filter_chunk: bad argument");
+    if ((in_dtype != DSTR_U16 && in_dtype != DSTR_F32) || (out_dtype != DSTR_U16 && out_dtype != DSTR_F32))
+        return fail(ctx, DSTR_E_ARG, "dstr_filter_chunk: bad dtype");
+    if (mode != DSTR_MODE_LOGSPACE && mode != DSTR_MODE_DISPATCH)
+        return fail(ctx, DSTR_E_ARG, "dstr_filter_chunk: bad mode");
+    if (mode == DSTR_MODE_DISPATCH && !cells)
+        return fail(ctx, DSTR_E_ARG, "dstr_filter_chunk: dispatch mode needs both parameter sets");
+    if ((flags & DSTR_FLAG_SHADOW) && !ctx->have_flat_dark)
+        return fail(ctx, DSTR_E_STATE, "dstr_filter_chunk: shadow correction requested without flat/dark");
+    if ((flags & DSTR_FLAG_STACK_OTSU) && mode == DSTR_MODE_DISPATCH)
+        return fail(ctx, DSTR_E_UNSUPPORTED, "stack-wide Otsu is only defined for log-space mode");
+    dstr_params pc = cells ? *cells : *no_cells;
+    dstr_params pn = *no_cells;
+    if (mode == DSTR_MODE_LOGSPACE) pc = pn;
+    if (!(pn.sigma > 0.f) || !(pc.sigma > 0.f))
+        return fail(ctx, DSTR_E_ARG, "sigma must be positive");  // notch(): filtering.py:111-112
+    int L = pn.level < 0 ? ctx->Lmax : pn.level;
+    const int Lc = pc.level < 0 ? ctx->Lmax : pc.level;
+    if (Lc != L)
+        return fail(ctx, DSTR_E_UNSUPPORTED,
+                    "cells/no_cells use different decomposition levels: split the chunk by config");
+    if (L > ctx->Lmax)
+        return fail(ctx, DSTR_E_UNSUPPORTED, "level exceeds pywt.dwtn_max_level for this plane shape");
+    CK(ctx, cudaSetDevice(ctx->device));
+
+    for (int l = 1; l <= L; ++l) {
+        int rc = build_taps(ctx, l, pc.sigma, pn.sigma);
+        if (rc) return rc;
+    }
+
+    const bool in_dev = is_device_ptr(in);
+    const bool out_dev = is_device_ptr(out);
+    const size_t plane_px = (size_t)ctx->H * ctx->W;
+    const size_t in_pb = plane_px * dtype_size(in_dtype);
+    const size_t out_pb = plane_px * dtype_size(out_dtype);
+    const bool stack = (flags & DSTR_FLAG_STACK_OTSU) != 0;
+    if (stack && Z > ctx->zcap)
+        return fail(ctx, DSTR_E_SHAPE, "stack-wide Otsu needs the whole chunk within max_planes");
+
+    int rc = 0;
+    if (in_dev && out_dev) {
+        for (int z0 = 0; z0 < Z; z0 += ctx->zcap) {
+            const int zn = std::min(ctx->zcap, Z - z0);
+            rc = process_device(ctx, (const char*)in + (size_t)z0 * in_pb, in_dtype,
+                                (char*)out + (size_t)z0 * out_pb, out_dtype, zn, pc, pn, high_int, mode,
+                                flags, L);
+            if (rc) return rc;
+        }
+        if (!(flags & DSTR_FLAG_NO_SYNC) || ctx->profiling) {
+            CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+            resolve_timers(ctx);
+        }
+        return 0;
+    }
+
+    // ---- host buffers: three-stream pipeline over sub-chunks -----------------------------------------
+    int sub = ctx->subchunk > 0 ? ctx->subchunk : std::min(ctx->zcap, 16);
+    sub = std::min(sub, ctx->zcap);
+    if (stack) sub = Z;
+    rc = ensure_stage(ctx, sub);
+    if (rc) return rc;
+    int it = 0;
+    for (int z0 = 0; z0 < Z; z0 += sub, ++it) {
+        const int zn = std::min(sub, Z - z0);
+        const int b = it & 1;
+        const void* src = (const char*)in + (size_t)z0 * in_pb;
+        void* dst = (char*)out + (size_t)z0 * out_pb;
+        const void* dsrc = src;
+        void* ddst = dst;
+        if (!in_dev) {
+            // the previous use of staging buffer b must have been consumed by compute
+            if (it >= 2) CK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));
+            CK(ctx, cudaMemcpyAsync(ctx->d_in[b], src, in_pb * zn, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CK(ctx, cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+            CK(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
+            dsrc = ctx->d_in[b];
+        }
+        if (!out_dev) {
+            if (it >= 2) CK(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[b], 0));
+            ddst = ctx->d_out[b];
+        }
+        rc = process_device(ctx, dsrc, in_dtype, ddst, out_dtype, zn, pc, pn, high_int, mode, flags, L);
+        if (rc) return rc;
+        CK(ctx, cudaEventRecord(ctx->ev_comp[b], ctx->s_comp));
+        if (!out_dev) {
+            CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[b], 0));
+            CK(ctx, cudaMemcpyAsync(dst, ctx->d_out[b], out_pb * zn, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+        }
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    resolve_timers(ctx);
+    return 0;
+}
+
+int dstr_plane_stats(dstr_ctx* ctx, const void* in, int in_dtype, int Z, double* fg_mean,
+                     double* bg_mean, int* use_cells, float high_int, float threshold_mask) {
+    if (!ctx) return DSTR_E_ARG;
+    if (!in || Z <= 0 || !fg_mean || !bg_mean) return fail(ctx, DSTR_E_ARG, "dstr_plane_stats: bad argument");
+    if (in_dtype != DSTR_U16 && in_dtype != DSTR_F32) return fail(ctx, DSTR_E_ARG, "bad dtype");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const bool in_dev = is_device_ptr(in);
+    const size_t plane_px = (size_t)ctx->H * ctx->W;
+    const size_t in_pb = plane_px * dtype_size(in_dtype);
+    int sub = std::min(ctx->zcap, Z);
+    if (!in_dev) {
+        int rc = ensure_stage(ctx, sub);
+        if (rc) return rc;
+    }
+    std::vector<PlaneStat> hs(sub);
+    const float fg_thr = (threshold_mask == 0.3f) ? ctx->fg_half_thr : find_fg_half_threshold(threshold_mask);
+    for (int z0 = 0; z0 < Z; z0 += sub) {
+        const int zn = std::min(sub, Z - z0);
+        const void* src = (const char*)in + (size_t)z0 * in_pb;
+        if (!in_dev) {
+            CK(ctx, cudaMemcpyAsync(ctx->d_in[0], src, in_pb * zn, cudaMemcpyHostToDevice, ctx->s_comp));
+            src = ctx->d_in[0];
+        }
+        CK(ctx, cudaMemsetAsync(ctx->d_pstat, 0, sizeof(PlaneStat) * zn, ctx->s_comp));
+        dim3 grid(std::max(1, (int)std::min<size_t>(plane_px / 4096 + 1, 592)), zn);
+        if (in_dtype == DSTR_U16)
+            plane_stats_kernel<uint16_t><<<grid, 256, 0, ctx->s_comp>>>((const uint16_t*)src, ctx->H, ctx->W,
+                                                                         plane_px, ctx->d_pstat, fg_thr);
+        else
+            plane_stats_kernel<float><<<grid, 256, 0, ctx->s_comp>>>((const float*)src, ctx->H, ctx->W, plane_px,
+                                                                      ctx->d_pstat, fg_thr);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaMemcpyAsync(hs.data(), ctx->d_pstat, sizeof(PlaneStat) * zn, cudaMemcpyDeviceToHost, ctx->s_comp));
+        CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+        for (int i = 0; i < zn; ++i) {
+            const double fg = hs[i].fg_cnt ? hs[i].fg_sum / (double)hs[i].fg_cnt : 0.0;
+            const double bg = hs[i].bg_cnt ? hs[i].bg_sum / (double)hs[i].bg_cnt : 0.0;
+            fg_mean[z0 + i] = fg;
+            bg_mean[z0 + i] = bg;
+            if (use_cells) use_cells[z0 + i] = (fg > bg && fg > (double)high_int) ? 1 : 0;
+        }
+    }
+    return 0;
+}
+
+int dstr_flatfield_correction(int device, const float* img, const float* flat, const float* dark,
+                              const float* baseline, uint16_t* out, int n_outer, int n_inner_h,
+                              int n_inner_w) {
+    if (!img || !flat || !dark || !out || n_outer <= 0 || n_inner_h <= 0 || n_inner_w <= 0)
+        return fail(nullptr, DSTR_E_ARG, "dstr_flatfield_correction: bad argument");
+    dstr_ctx* ctx = nullptr;
+    CK(ctx, cudaSetDevice(device));
+    const size_t inner = (size_t)n_inner_h * n_inner_w, n = inner * n_outer;
+    float *d_img = nullptr, *d_flat = nullptr, *d_dark = nullptr, *d_base = nullptr;
+    unsigned short* d_out = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_img);
+        cudaFree(d_flat);
+        cudaFree(d_dark);
+        cudaFree(d_base);
+        cudaFree(d_out);
+    };
+#define CKF(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            rc = fail(nullptr, (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            cleanup();                                                                     \
+            return rc;                                                                     \
+        }                                                                                  \
+    } while (0)
+    CKF(cudaMalloc(&d_img, n * 4));
+    CKF(cudaMalloc(&d_flat, n * 4));
+    CKF(cudaMalloc(&d_dark, n * 4));
+    CKF(cudaMalloc(&d_out, n * 2));
+    CKF(cudaMemcpy(d_img, img, n * 4, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_flat, flat, n * 4, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_dark, dark, n * 4, cudaMemcpyHostToDevice));
+    if (baseline) {
+        CKF(cudaMalloc(&d_base, (size_t)n_outer * 4));
+        CKF(cudaMemcpy(d_base, baseline, (size_t)n_outer * 4, cudaMemcpyHostToDevice));
+    }
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    flatfield_kernel<<<blocks, 256>>>(d_img, d_flat, d_dark, d_base, d_out, (size_t)n_outer, inner);
+    CKF(cudaGetLastError());
+    CKF(cudaMemcpy(out, d_out, n * 2, cudaMemcpyDeviceToHost));
+#undef CKF
+    cleanup();
+    return 0;
+}
+
+int dstr_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return DSTR_E_ARG;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, (int)e, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return 0;
+}
+int dstr_host_free(void* ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaFreeHost(ptr);
+    return e == cudaSuccess ? 0 : fail(nullptr, (int)e, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
+}
+int dstr_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return DSTR_E_ARG;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    return e == cudaSuccess ? 0 : fail(nullptr, (int)e, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+}
+int dstr_host_unregister(void* ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaHostUnregister(ptr);
+    return e == cudaSuccess ? 0 : fail(nullptr, (int)e, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+}
+
+int dstr_device_alloc(dstr_ctx* ctx, void** ptr, uint64_t bytes) {
+    if (!ctx || !ptr || bytes == 0) return DSTR_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMalloc(ptr, bytes));
+    return 0;
+}
+int dstr_device_free(dstr_ctx* ctx, void* ptr) {
+    if (!ctx) return DSTR_E_ARG;
+    if (!ptr) return 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFree(ptr));
+    return 0;
+}
+int dstr_memcpy_h2d(dstr_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx || !dst || !src) return DSTR_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    return 0;
+}
+int dstr_memcpy_d2h(dstr_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx || !dst || !src) return DSTR_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    return 0;
+}
+int dstr_synchronize(dstr_ctx* ctx) {
+    if (!ctx) return DSTR_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    resolve_timers(ctx);
+    return 0;
+}
+void* dstr_compute_stream(dstr_ctx* ctx) { return ctx ? (void*)ctx->s_comp : nullptr; }
+
+int dstr_set_profiling(dstr_ctx* ctx, int enabled) {
+    if (!ctx) return DSTR_E_ARG;
+    ctx->profiling = enabled != 0;
+    return 0;
+}
+int dstr_get_timers(dstr_ctx* ctx, double* ms_out, uint64_t* launches_out) {
+    if (!ctx) return DSTR_E_ARG;
+    if (ms_out) std::memcpy(ms_out, ctx->timers, sizeof(ctx->timers));
+    if (launches_out) *launches_out = ctx->launches;
+    return 0;
+}
+int dstr_reset_timers(dstr_ctx* ctx) {
+    if (!ctx) return DSTR_E_ARG;
+    std::memset(ctx->timers, 0, sizeof(ctx->timers));
+    ctx->launches = 0;
+    return 0;
+}
+int dstr_set_debug_stop(dstr_ctx* ctx, int stage) {
+    if (!ctx || stage < DSTR_STAGE_NONE || stage > DSTR_STAGE_SYNTH) return DSTR_E_ARG;
+    ctx->debug_stop = stage;
+    return 0;
+}
+int dstr_set_subchunk(dstr_ctx* ctx, int planes) {
+    if (!ctx || planes < 0) return DSTR_E_ARG;
+    ctx->subchunk = planes;
+    return 0;
+}
+
+int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_t host_bytes) {
+    if (!ctx || !host_buf) return DSTR_E_ARG;
+    if (level < 1 || level > ctx->Lmax) return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: bad level");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    const int Z = ctx->last_z;
+    const LevelGeom& g = ctx->geom[level];
+    if (what == DSTR_FETCH_CA || what == DSTR_FETCH_CH) {
+        const size_t need = sizeof(float) * (size_t)Z * g.H * g.W;
+        if (host_bytes < need) return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: buffer too small");
+        const float* src = (what == DSTR_FETCH_CA) ? ctx->d_A[level] : ctx->d_H[level];
+        for (int z = 0; z < Z; ++z) {
+            CK(ctx, cudaMemcpy2D((float*)host_buf + (size_t)z * g.H * g.W, sizeof(float) * g.W,
+                                 src + (size_t)z * g.pstride, sizeof(float) * g.pitch, sizeof(float) * g.W,
+                                 g.H, cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    }
+    std::vector<LevelStat> ls(Z);
+    std::vector<PlaneStat> ps(Z);
+    CK(ctx, cudaMemcpy(ls.data(), ctx->d_lstat + (size_t)(level - 1) * ctx->zcap, sizeof(LevelStat) * Z,
+                       cudaMemcpyDeviceToHost));
+    CK(ctx, cudaMemcpy(ps.data(), ctx->d_pstat, sizeof(PlaneStat) * Z, cudaMemcpyDeviceToHost));
+    if (what == DSTR_FETCH_STATS) {
+        if (host_bytes < sizeof(float) * 8 * (size_t)Z) return fail(ctx, DSTR_E_ARG, "buffer too small");
+        float* o = (float*)host_buf;
+        for (int z = 0; z < Z; ++z) {
+            unsigned mn = ~ls[z].qmin_inv, mx = ls[z].qmax_bits;
+            float fmn, fmx;
+            std::memcpy(&fmn, &mn, 4);
+            std::memcpy(&fmx, &mx, 4);
+            const double fg = ps[z].fg_cnt ? ps[z].fg_sum / (double)ps[z].fg_cnt : 0.0;
+            const double bg = ps[z].bg_cnt ? ps[z].bg_sum / (double)ps[z].bg_cnt : 0.0;
+            o[8 * z + 0] = fmn;
+            o[8 * z + 1] = fmx;
+            o[8 * z + 2] = ls[z].otsu_raw;
+            o[8 * z + 3] = ls[z].thr;
+            o[8 * z + 4] = 0.f;
+            o[8 * z + 5] = (float)fg;
+            o[8 * z + 6] = (float)bg;
+            o[8 * z + 7] = (float)ls[z].otsu_bin;
+        }
+        return 0;
+    }
+    if (what == DSTR_FETCH_HIST) {
+        if (host_bytes < sizeof(unsigned) * 256 * (size_t)Z) return fail(ctx, DSTR_E_ARG, "buffer too small");
+        for (int z = 0; z < Z; ++z) std::memcpy((unsigned*)host_buf + 256 * z, ls[z].hist, sizeof(unsigned) * 256);
+        return 0;
+    }
+    return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: unknown item");
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""Reference-compatible filter entry points backed by the B200 CUDA engine.
+
+Same names, positional order, defaults and exception types as
+``/root/reference/code/aind_smartspim_destripe/filtering.py``:
+
+* ``filter_stripes`` (:417-491), ``log_space_fft_filtering`` (:139-224),
+  ``get_foreground_background_mean`` (:54-88), ``flatfield_correction`` (:338-414)
+  run on the GPU through ``libdstr_b200.so``; there is no CPU fallback.
+* ``sigmoid`` (:13-22), ``foreground_fraction`` (:25-51), ``notch`` (:91-115),
+  ``gaussian_filter`` (:118-136), ``normalize_image`` (:227-250), ``invert_image``
+  (:253-270), ``get_hemisphere_flatfield`` (:273-335) are O(plane) or O(row) host helpers
+  that sit outside the hot path (once-per-tile preparation / table generation) and stay
+  in numpy.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import engine as _eng
+
+
+# --------------------------------------------------------------------------- host helpers
+def sigmoid(data: np.ndarray):
+    """1 / (1 + exp(-data))  (reference filtering.py:13-22)."""
+    return 1 / (1 + np.exp(-data))
+
+
+def foreground_fraction(img: np.ndarray, center: float, crossover: float):
+    """sigmoid((img - center) / crossover)  (reference filtering.py:25-51)."""
+    return sigmoid((img - center) / crossover)
+
+
+def notch(n, sigma):
+    """1-D Gaussian notch ``1 - exp(-k^2 / (2 sigma^2))`` (reference filtering.py:91-115)."""
+    if n <= 0:
+        raise ValueError("n must be positive")
+    n = int(n)
+    if sigma <= 0:
+        raise ValueError("sigma must be positive")
+    k = np.arange(n)
+    return 1 - np.exp(-(k**2) / (2 * sigma**2))
+
+
+def gaussian_filter(shape, sigma):
+    """``notch`` broadcast over ``shape`` (reference filtering.py:118-136)."""
+    return np.broadcast_to(notch(n=shape[-1], sigma=sigma), shape).copy()
+
+
+def normalize_image(images: List[np.ndarray]) -> np.ndarray:
+    """Normalise to [1, 2] as float16 (reference filtering.py:227-250)."""
+    images = np.array(images)
+    lo, hi = np.min(images), np.max(images)
+    return 1 + np.divide(images - lo, hi - lo).astype(np.float16)
+
+
+def invert_image(image: np.ndarray) -> np.ndarray:
+    """``max - image`` (reference filtering.py:253-270)."""
+    image = np.array(image)
+    return image.max() - image
+
+
+def get_hemisphere_flatfield(input_tile_path, tile_config: dict, flatfields, zarr: Optional[bool] = True):
+    """Pick the flat field of the tile's laser side (reference filtering.py:273-335)."""
+    if zarr:
+        parts = str(input_tile_path).split("_")
+    else:
+        parts = str(input_tile_path).split("/")[-2].split("_")
+    x_folder, y_folder = parts[0], parts[1]
+    if tile_config.get(x_folder) is None:
+        raise KeyError(f"Please, check the tile config while trying to reach: {x_folder}")
+    side = tile_config[x_folder].get(y_folder)
+    if side is None:
+        raise KeyError(f"Please, check the tile config while trying to reach: {y_folder}")
+    return flatfields[side]
+
+
+# --------------------------------------------------------------------------- GPU-backed API
+def _as_engine_planes(image: np.ndarray) -> np.ndarray:
+    """uint16 / float32 pass through; every other dtype is converted to float32."""
+    image = np.asarray(image)
+    if image.dtype == np.uint16 or image.dtype == np.float32:
+        return np.ascontiguousarray(image)
+    return np.ascontiguousarray(image, dtype=np.float32)
+
+
+def get_foreground_background_mean(img: np.ndarray, threshold_mask: Optional[float] = 0.3) -> Tuple:
+    """(fg_mean, bg_mean, mask): reference filtering.py:54-88.
+
+    The two class means are reduced on the GPU (``dstr_plane_stats``); the float16 sigmoid rule
+    ``sigmoid((float16(v) - 400) / 20) > threshold_mask`` is monotone in ``float16(v)``, so the
+    device applies it as a threshold on the float16-rounded pixel value.
+    """
+    img = np.asarray(img)
+    if img.size == 0:
+        return 0.0, 0.0, np.zeros(img.shape, dtype=np.float16)
+    planes = _as_engine_planes(img)
+    planes = planes.reshape(1, -1, planes.shape[-1]) if planes.ndim >= 2 else planes.reshape(1, 1, -1)
+    eng = _eng.get_engine(planes.shape[1], planes.shape[2])
+    fg, bg, _ = eng.plane_stats(planes, threshold_mask=threshold_mask)
+    # the 0/1 float16 mask the reference also returns (unused by its callers)
+    thr = np.float32(_eng.foreground_threshold(threshold_mask))
+    with np.errstate(over="ignore"):
+        mask = (img.astype(np.float16).astype(np.float32) >= thr).astype(np.float16)
+    return float(fg[0]), float(bg[0]), mask
+
+
+def log_space_fft_filtering(
+    input_image: np.ndarray,
+    wavelet: Optional[str] = "db3",
+    level: Optional[int] = 0,
+    sigma: Optional[int] = 64,
+    max_threshold: Optional[int] = 4,
+):
+    """Log-space wavelet-FFT streak filter (reference filtering.py:139-224) on the GPU.
+
+    2-D input: one plane.  3-D input ``(Z, H, W)``: the reference's stack semantics (one Otsu
+    threshold per level for the whole stack).  Returns float64 ``exp(y) + 1`` like the
+    reference (computed in float32 on the device).
+    """
+    input_image = np.asarray(input_image)
+    if input_image.ndim < 2:
+        raise ValueError("Expected input data to have at least 2 dimensions.")
+    if input_image.ndim > 3:
+        raise NotImplementedError("B200 engine: only 2-D planes and 3-D stacks are supported")
+    params = _eng.make_params(dict(wavelet=wavelet, level=level, sigma=sigma, max_threshold=max_threshold))
+    planes = _as_engine_planes(input_image)
+    stack = planes.ndim == 3
+    if not stack:
+        planes = planes[None]
+    Z, H, W = planes.shape
+    eng = _eng.get_engine(H, W, max_planes=max(16, Z) if stack else 16)
+    flags = _eng.FLAG_STACK_OTSU if stack and Z > 1 else 0
+    out = eng.filter_chunk(planes, params, out_dtype=np.float32, mode=_eng.MODE_LOGSPACE, flags=flags)
+    out = out.astype(np.float64)
+    return out if stack else out[0]
+
+
+def flatfield_correction(
+    image_tiles: List[np.ndarray],
+    flatfield: np.ndarray,
+    darkfield: np.ndarray,
+    baseline: Optional[np.ndarray] = None,
+) -> np.ndarray:
+    """Dark/flat correction, clip, truncate to uint16 (reference filtering.py:338-414)."""
+    image_tiles = np.array(image_tiles)
+    flatfield = np.asarray(flatfield)
+    darkfield = np.asarray(darkfield)
+    if image_tiles.ndim != flatfield.ndim:
+        flatfield = np.expand_dims(flatfield, axis=0)
+    if image_tiles.ndim != darkfield.ndim:
+        darkfield = np.expand_dims(darkfield, axis=0)
+    darkfield = darkfield[: image_tiles.shape[-2], : image_tiles.shape[-1]]
+    if darkfield.shape != image_tiles.shape:
+        raise ValueError(
+            "Please, check the shape of the darkfield. "
+            f"Image: {image_tiles.shape} - Darkfield: {darkfield.shape}"
+        )
+    if flatfield.shape != image_tiles.shape:
+        raise ValueError(
+            "Please, check the shape of the flatfield."
+            f"Image: {image_tiles.shape} - Flatfield: {flatfield.shape}"
+        )
+    n_outer = image_tiles.shape[0]
+    inner = int(np.prod(image_tiles.shape[1:])) if image_tiles.ndim > 1 else 1
+    img32 = np.ascontiguousarray(image_tiles, dtype=np.float32)
+    flat32 = np.ascontiguousarray(flatfield, dtype=np.float32)
+    dark32 = np.ascontiguousarray(darkfield, dtype=np.float32)
+    base_ptr = None
+    if baseline is not None:
+        base32 = np.ascontiguousarray(baseline, dtype=np.float32)
+        if base32.shape != (n_outer,):
+            raise ValueError("baseline must have one entry per leading index of image_tiles")
+        base_ptr = base32.ctypes.data_as(C.c_void_p)
+    out = np.empty(image_tiles.shape, dtype=np.uint16)
+    lib = _eng.load_library()
+    rc = lib.dstr_flatfield_correction(
+        _eng.default_device(),
+        img32.ctypes.data_as(C.c_void_p),
+        flat32.ctypes.data_as(C.c_void_p),
+        dark32.ctypes.data_as(C.c_void_p),
+        base_ptr,
+        out.ctypes.data_as(C.c_void_p),
+        int(n_outer),
+        int(inner),
+        1,
+    )
+    if rc:
+        _eng._raise(rc, None, "dstr_flatfield_correction")
+    return out
+
+
+def _resolve_shadow(shadow_correction: dict, input_tile_path, shape):
+    """flat (H, W) float32 / dark (H, W) float32 for the fused epilogue (filtering.py:470-489)."""
+    retrospective = shadow_correction.get("retrospective")
+    flatfield = shadow_correction.get("flatfield")
+    darkfield = shadow_correction.get("darkfield")
+    tile_config = shadow_correction.get("tile_config")
+    if not retrospective:
+        flatfield = get_hemisphere_flatfield(
+            input_tile_path=input_tile_path, tile_config=tile_config, flatfields=flatfield
+        )
+    flatfield = np.asarray(flatfield)
+    darkfield = np.asarray(darkfield)
+    H, W = shape
+    dark_c = darkfield[:H, :W]  # filtering.py:377
+    if dark_c.shape != (H, W):
+        raise ValueError(
+            f"Please, check the shape of the darkfield. Image: {(H, W)} - Darkfield: {dark_c.shape}"
+        )
+    if flatfield.shape != (H, W):
+        raise ValueError(
+            f"Please, check the shape of the flatfield.Image: {(H, W)} - Flatfield: {flatfield.shape}"
+        )
+    return flatfield, darkfield, dark_c
+
+
+_shadow_cache = {}
+
+
+def _engine_with_shadow(eng, shadow_correction, input_tile_path, shape):
+    flat, dark_full, dark_c = _resolve_shadow(shadow_correction, input_tile_path, shape)
+    key = (id(eng), id(flat), id(dark_full))
+    cached = _shadow_cache.get(id(eng))
+    if cached is None or cached[0] != key:
+        f32 = np.ascontiguousarray(flat, dtype=np.float32)
+        d32 = np.ascontiguousarray(dark_c, dtype=np.float32)
+        eng.set_flat_dark(f32, d32)
+        _shadow_cache[id(eng)] = (key, flat, dark_full, f32, d32)  # keep the ids alive
+
+
+def filter_planes(
+    planes: np.ndarray,
+    input_tile_path,
+    no_cells_config: dict,
+    cells_config: dict,
+    shadow_correction: Optional[dict] = None,
+    microscope_high_int: Optional[int] = 2700,
+    out: Optional[np.ndarray] = None,
+    engine: Optional["_eng.DestripeEngine"] = None,
+) -> np.ndarray:
+    """``filter_stripes`` for a whole (Z, H, W) chunk in one engine call.
+
+    Result ``[z]`` equals ``filter_stripes(planes[z], ...)``: uint16 when ``shadow_correction``
+    is given, float32 ``exp(y) + 1`` otherwise.
+    """
+    planes = _as_engine_planes(planes)
+    if planes.ndim != 3:
+        raise ValueError("filter_planes expects a (Z, H, W) array")
+    Z, H, W = planes.shape
+    pn = _eng.make_params(no_cells_config)
+    pc = _eng.make_params(cells_config)
+    eng = engine if engine is not None else _eng.get_engine(H, W)
+    flags = 0
+    out_dtype = np.float32
+    if shadow_correction is not None:
+        _engine_with_shadow(eng, shadow_correction, input_tile_path, (H, W))
+        flags |= _eng.FLAG_SHADOW
+        out_dtype = np.uint16
+    if out is None:
+        out = np.empty((Z, H, W), dtype=out_dtype)
+
+    lc = eng.max_level if pc.level < 0 else pc.level
+    ln = eng.max_level if pn.level < 0 else pn.level
+    if lc == ln:
+        return eng.filter_chunk(
+            planes, pn, cells=pc, out=out, high_int=microscope_high_int, mode=_eng.MODE_DISPATCH, flags=flags
+        )
+    # the two configs decompose to different depths: group planes by the dispatch decision
+    _, _, use_cells = eng.plane_stats(planes, high_int=microscope_high_int)
+    for flag, params in ((0, pn), (1, pc)):
+        idx = np.nonzero(use_cells == flag)[0]
+        if idx.size == 0:
+            continue
+        res = eng.filter_chunk(
+            np.ascontiguousarray(planes[idx]), params, out_dtype=out.dtype, mode=_eng.MODE_LOGSPACE, flags=flags
+        )
+        out[idx] = res
+    return out
+
+
+def filter_stripes(
+    image: np.ndarray,
+    input_tile_path: str,
+    no_cells_config: dict,
+    cells_config: dict,
+    shadow_correction: Optional[dict] = None,
+    microscope_high_int: Optional[int] = 2700,
+) -> np.ndarray:
+    """Per-plane destripe with cells / no-cells dispatch (reference filtering.py:417-491).
+
+    Returns uint16 when ``shadow_correction`` is a dict, else float64 ``exp(y) + 1``.
+    """
+    image = np.asarray(image)
+    if image.ndim != 2:
+        raise NotImplementedError("B200 engine: filter_stripes expects one 2-D plane")
+    out = filter_planes(
+        image[None], input_tile_path, no_cells_config, cells_config, shadow_correction, microscope_high_int
+    )[0]
+    if shadow_correction is None:
+        return out.astype(np.float64)
+    return out

@@ -1,0 +1,155 @@
+/*
+ * dstr_b200.h - C-ABI of the B200-native destripe engine (libdstr_b200.so).
+ *
+ * Drop-in boundary for the per-plane streak-removal hot path of
+ * AllenNeuralDynamics/aind-smartspim-destripe.  The reference is pure Python, so the
+ * binding a maintainer adds is a ctypes stub; every entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes only; no
+ * torch / numpy types.  All functions return 0 on success, a negative DSTR_E_* code for
+ * an invalid argument, or a positive cudaError_t value; dstr_last_error() gives text.
+ *
+ * Threading: one dstr_ctx per host thread per GPU.  A context owns its device workspace
+ * and CUDA streams; calls on one context are serialised by the caller, calls on
+ * different contexts are independent (reference: one OS process per plane worker,
+ * zarr_destriper.py:1151-1165).
+ */
+#ifndef DSTR_B200_H
+#define DSTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dstr_ctx dstr_ctx;
+
+/* element types of caller buffers */
+#define DSTR_U16 0
+#define DSTR_F32 1
+
+/* error codes (negative) */
+#define DSTR_E_ARG -1       /* bad argument (NULL, non-positive size, bad dtype ...)      */
+#define DSTR_E_SHAPE -2     /* plane shape unsupported by this context                    */
+#define DSTR_E_STATE -3     /* call not valid in the current state (e.g. no flat/dark)    */
+#define DSTR_E_UNSUPPORTED -4
+
+/* mode of dstr_filter_chunk */
+#define DSTR_MODE_LOGSPACE 0 /* every plane filtered with `no_cells` (filtering.py:139-224) */
+#define DSTR_MODE_DISPATCH 1 /* per-plane cells / no_cells choice (filtering.py:459-467)    */
+
+/* flags of dstr_filter_chunk */
+#define DSTR_FLAG_SHADOW 1      /* dark/flat epilogue + clip + truncate (filtering.py:338-414) */
+#define DSTR_FLAG_EXPM1 2       /* corrected inverse exp(y)-1 instead of the reference's exp(y)+1 */
+#define DSTR_FLAG_STACK_OTSU 4  /* 3-D input semantics: one Otsu threshold per level for the whole
+                                   chunk (filtering.py:182-183,210-213)                          */
+#define DSTR_FLAG_NO_SYNC 8     /* device buffers only: enqueue and return without synchronising */
+
+/* Filter parameters = the reference's config dict {wavelet:"db3", level, sigma, max_threshold}
+ * (run_capsule.py:377-388).  level < 0 means "None" (maximum level). */
+typedef struct dstr_params {
+    float sigma;
+    float max_threshold;
+    int level;
+} dstr_params;
+
+/* debug stages for dstr_set_debug_stop / dstr_debug_fetch */
+#define DSTR_STAGE_NONE 0
+#define DSTR_STAGE_ANALYSIS 1 /* stop after all DWT analysis levels (cA_l, cH_l valid)        */
+#define DSTR_STAGE_OTSU 2     /* + min/max, histograms, thresholds                           */
+#define DSTR_STAGE_FILTER 3   /* + cH_l replaced by dH_l = cH'_l - cH_l                      */
+#define DSTR_STAGE_SYNTH 4    /* + cA_l replaced by dA_l for l < L (all but the final level) */
+
+/* what to fetch */
+#define DSTR_FETCH_CA 0    /* float32 [Z][H_l][W_l] approximation (or dA_l after SYNTH)       */
+#define DSTR_FETCH_CH 1    /* float32 [Z][H_l][W_l] horizontal detail (or dH_l after FILTER)  */
+#define DSTR_FETCH_STATS 2 /* float32 [Z][8]: qmin, qmax, otsu_raw, threshold, use_cells, fg_mean,
+                              bg_mean, otsu_bin (level-independent entries repeated)           */
+#define DSTR_FETCH_HIST 3  /* uint32 [Z][256] histogram of cH_l^2                             */
+
+/* ---- lifetime -------------------------------------------------------------------------
+ * Replaces: worker-process start-up (zarr_destriper.py:1151-1165).  A context is sized for
+ * chunks of at most `max_planes` planes of exactly H x W pixels. */
+int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out);
+int dstr_destroy(dstr_ctx* ctx);
+const char* dstr_last_error(const dstr_ctx* ctx); /* ctx may be NULL: last global error */
+
+/* ---- shadow-correction fields ----------------------------------------------------------
+ * Replaces: shadow_correction["flatfield"/"darkfield"] handed to flatfield_correction
+ * (filtering.py:470-489, :338-414).  Host pointers, H*W elements each, already cropped to
+ * the plane shape (filtering.py:377); NULL clears.  Copied to the device. */
+int dstr_set_flat_dark(dstr_ctx* ctx, const float* flat, const float* dark);
+
+/* ---- the hot path -----------------------------------------------------------------------
+ * Replaces: the plane loop of execute_worker (zarr_destriper.py:319-327) calling
+ * filter_stripes (filtering.py:417-491) / log_space_fft_filtering (filtering.py:139-224).
+ *   in      : Z planes of H*W elements, contiguous, dtype in_dtype; host or device pointer
+ *   out     : Z planes, dtype out_dtype (DSTR_U16: clip [0,65535] + truncate; DSTR_F32: raw)
+ *   cells / no_cells : parameter sets; `cells` may be NULL in DSTR_MODE_LOGSPACE
+ *   high_int: microscope_high_int of filter_stripes (2500 in the Zarr path)
+ * Host buffers are streamed through the device in sub-chunks with H2D / compute / D2H
+ * overlapped on three CUDA streams (replaces producer/consumer, zarr_destriper.py:797-906);
+ * pinned host memory (dstr_host_alloc / dstr_host_register) makes the copies asynchronous. */
+int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, int out_dtype, int Z,
+                      const dstr_params* cells, const dstr_params* no_cells, float high_int,
+                      int mode, int flags);
+
+/* Replaces: get_foreground_background_mean (filtering.py:54-88) for Z planes at once.
+ * fg_mean / bg_mean: host arrays of Z doubles (0.0 when the class is empty); use_cells
+ * (nullable): the filter_stripes decision fg > bg && fg > high_int (filtering.py:462);
+ * threshold_mask: the reference's keyword (0.3 in the hot path). */
+int dstr_plane_stats(dstr_ctx* ctx, const void* in, int in_dtype, int Z, double* fg_mean,
+                     double* bg_mean, int* use_cells, float high_int, float threshold_mask);
+
+/* Replaces: flatfield_correction (filtering.py:338-414) as a standalone call.  Host pointers;
+ * img / flat / dark hold n_outer * H * W float32 elements (identical shapes, as the reference
+ * requires, filtering.py:379-391); baseline is n_outer floats or NULL (zeros);
+ * out = uint16( trunc( clip( (img <= dark ? 0 : img - dark) / flat - baseline, 0, 65535 ) ) ). */
+int dstr_flatfield_correction(int device, const float* img, const float* flat, const float* dark,
+                              const float* baseline, uint16_t* out, int n_outer, int H, int W);
+
+/* ---- geometry / tables (host only, no GPU work) ---------------------------------------------
+ * Replaces: pywt.dwtn_max_level / dwt_coeff_len bookkeeping behind pywt.wavedec2
+ * (filtering.py:176). */
+int dstr_max_level(int H, int W);
+int dstr_level_shape(int H, int W, int level, int* H_l, int* W_l);
+/* Smallest float16 value v with sigmoid((v - 400) / 20) > threshold_mask under float16
+ * arithmetic, i.e. the foreground rule of get_foreground_background_mean (filtering.py:78-81)
+ * as a threshold on float16(pixel); -inf / +inf when the rule holds everywhere / nowhere. */
+float dstr_foreground_threshold(float threshold_mask);
+/* Time-domain form of the reference's packed-rfft notch (filtering.py:206-215):
+ * irfft(rfft(x) * g) = x - B x with B[t][v] = hp[(t - v) mod n] + hq[(t + v) mod n].
+ * Writes n doubles to each of hp, hq. */
+int dstr_notch_kernels(int n, double s, double* hp, double* hq);
+
+/* ---- pinned host memory ---------------------------------------------------------------------- */
+int dstr_host_alloc(void** ptr, uint64_t bytes);
+int dstr_host_free(void* ptr);
+int dstr_host_register(void* ptr, uint64_t bytes);
+int dstr_host_unregister(void* ptr);
+
+/* ---- device memory (for callers that keep chunks resident, e.g. the benchmark) ------------- */
+int dstr_device_alloc(dstr_ctx* ctx, void** ptr, uint64_t bytes);
+int dstr_device_free(dstr_ctx* ctx, void* ptr);
+int dstr_memcpy_h2d(dstr_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int dstr_memcpy_d2h(dstr_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int dstr_synchronize(dstr_ctx* ctx);
+/* cudaStream_t of the compute stream (so a caller can record its own events on it) */
+void* dstr_compute_stream(dstr_ctx* ctx);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+#define DSTR_NUM_TIMERS 8
+/* timers: 0 analysis L1, 1 analysis L2+, 2 histogram, 3 otsu, 4 row filter, 5 synthesis L2+,
+ *         6 final synthesis+epilogue, 7 whole chunk (device time, ms, accumulated). */
+int dstr_set_profiling(dstr_ctx* ctx, int enabled);
+int dstr_get_timers(dstr_ctx* ctx, double* ms_out /*[DSTR_NUM_TIMERS]*/, uint64_t* launches_out);
+int dstr_reset_timers(dstr_ctx* ctx);
+int dstr_set_debug_stop(dstr_ctx* ctx, int stage);
+int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_t host_bytes);
+/* sub-chunk size (planes) used when streaming host buffers; 0 restores the default */
+int dstr_set_subchunk(dstr_ctx* ctx, int planes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSTR_B200_H */

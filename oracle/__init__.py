@@ -1,0 +1,26 @@
+"""CPU oracle for the aind-smartspim-destripe plane-filter hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it, and there only as the checker or the
+timed CPU baseline.  The product package ``aind_smartspim_destripe_b200`` never
+imports this package and has no CPU fallback.
+
+What it restates (numpy + scipy.fftpack, dtype-faithful):
+
+* ``/root/reference/code/aind_smartspim_destripe/filtering.py:13-224`` and
+  ``:338-491`` (sigmoid .. filter_stripes)            -> ``oracle.plane_filter``
+* ``zarr_destriper.py:253-336`` (execute_worker)         -> ``oracle.worker``
+* PyWavelets==1.6.0 ``wavedec2/waverec2`` (not vendored) -> ``oracle.dwt``
+* scikit-image==0.24.0 ``threshold_otsu`` on top of
+  numpy==1.26.4 ``np.histogram`` semantics (not vendored)-> ``oracle.otsu``
+
+PARITY PINNING STATUS: *partially pinned*.  The helper functions are pinned by
+the reference's own known-answer unit tests (``code/tests/test_filtering.py``,
+re-hosted in ``tests/test_oracle_reference_kat.py``).  The DWT restatement is
+pinned by PyWavelets' documented known answers (db1/db2) and perfect
+reconstruction.  The *composition* pywt∘otsu∘fftpack inside
+``log_space_fft_filtering`` is pinned by NO reference test or golden vector
+(the reference only asserts shape/positivity) and pywt/skimage are not
+installable here, so for that composition this oracle is **parity unpinned**.
+"""

@@ -1,0 +1,164 @@
+"""GPU tests of the reference-facing API: filter_stripes dispatch + epilogue, the chunk worker,
+the streamed volume pipeline and the helper entry points, against the oracle."""
+import numpy as np
+import pytest
+
+from _parity import U16_FRACTION, u16_agreement
+from aind_smartspim_destripe_b200 import engine as E
+from aind_smartspim_destripe_b200 import filtering as fl
+from aind_smartspim_destripe_b200 import synthetic as S
+from aind_smartspim_destripe_b200 import zarr_destriper as zd
+from oracle import plane_filter as OF
+from oracle import worker as OW
+
+pytestmark = pytest.mark.gpu
+
+
+def _shadow(H, W, retrospective=True):
+    flat, dark = S.synthetic_flat_dark(H + 8, W + 8)
+    if retrospective:
+        return dict(retrospective=True, flatfield=flat[:H, :W].copy(), darkfield=dark, tile_config=None)
+    flat2 = (flat[:H, :W] * 1.1).astype(np.float32)
+    return dict(retrospective=False, flatfield=[flat[:H, :W].copy(), flat2], darkfield=dark,
+                tile_config={"10": {"20": 1, "30": 0}})
+
+
+def test_get_foreground_background_mean_known_answers():
+    # /root/reference/code/tests/test_filtering.py:41-114
+    fg, bg, mask = fl.get_foreground_background_mean(np.array([10, 20, 400, 500, 600]), 0.3)
+    assert fg == pytest.approx(500.0) and bg == pytest.approx(15.0)
+    np.testing.assert_array_equal(mask, [0, 0, 1, 1, 1])
+    fg, bg, mask = fl.get_foreground_background_mean(np.array([]), 0.3)
+    assert fg == 0.0 and bg == 0.0 and mask.size == 0
+    img = np.array([10, 20, 30, 40, 50])
+    fg, bg, mask = fl.get_foreground_background_mean(img, 1.0)
+    assert fg == 0.0 and bg == pytest.approx(img.mean())
+    np.testing.assert_array_equal(mask, np.zeros_like(img))
+    img = np.array([400, 420, 430, 440, 460])
+    fg, bg, mask = fl.get_foreground_background_mean(img, 0.0)
+    assert fg == pytest.approx(img.mean()) and bg == 0.0
+    np.testing.assert_array_equal(mask, np.ones_like(img))
+
+
+def test_plane_stats_match_oracle_on_planes():
+    st = S.synthetic_stack(4, 200, 240, cells_every=2)
+    eng = E.DestripeEngine(200, 240, max_planes=4)
+    fg, bg, uc = eng.plane_stats(st, high_int=2500)
+    for z in range(4):
+        rfg, rbg, _ = OF.get_foreground_background_mean(st[z].astype(np.float32))
+        assert fg[z] == pytest.approx(float(rfg), rel=1e-5) and bg[z] == pytest.approx(float(rbg), rel=1e-5)
+        assert uc[z] == int(rfg > rbg and rfg > 2500)
+    assert list(uc) == [0, 1, 0, 1]
+    eng.close()
+
+
+def test_flatfield_correction_known_answer():
+    # /root/reference/code/tests/test_filtering.py:226-240 (truncation, not rounding)
+    image_tiles = np.array([[[10, 20], [30, 40]]])
+    out = fl.flatfield_correction(image_tiles, np.array([[[2, 2], [2, 2]]]), np.array([[[1, 1], [1, 1]]]))
+    assert out.dtype == np.uint16
+    np.testing.assert_array_equal(out, np.array([[[4, 9], [14, 19]]], dtype=np.uint16))
+    rng = np.random.default_rng(0)
+    img = rng.uniform(0, 70000, (3, 40, 50))
+    flat = rng.uniform(1, 2, (3, 40, 50)).astype(np.float32)
+    dark = rng.integers(90, 110, (3, 40, 50)).astype(np.uint16)
+    ref = OF.flatfield_correction(img.astype(np.float32), flat, dark)
+    out = fl.flatfield_correction(img.astype(np.float32), flat, dark)
+    frac, mx, _ = u16_agreement(out, ref)
+    assert frac == 1.0 and mx <= 1
+
+
+@pytest.mark.parametrize("retrospective", [True, False])
+def test_filter_stripes_dispatch_and_shadow(retrospective, production_configs):
+    no_cells, cells = production_configs
+    H, W = 320, 400
+    st = S.synthetic_stack(2, H, W, base_seed=11, cells_every=2)
+    shadow = _shadow(H, W, retrospective)
+    tile = "10_20"
+    for z in range(2):
+        img = st[z].astype(np.float32)
+        ref = OF.filter_stripes(img, tile, no_cells, cells, shadow, 2500)
+        out = fl.filter_stripes(img, tile, no_cells, cells, shadow, 2500)
+        assert out.dtype == np.uint16 and out.shape == (H, W)
+        frac, mx, exact = u16_agreement(out, ref)
+        print(f"filter_stripes plane {z} retrospective={retrospective}: within+-1 {frac:.6f} exact {exact:.4f} max {mx}")
+        assert frac >= U16_FRACTION
+        ref_f = OF.filter_stripes(img, tile, no_cells, cells, None, 2500)
+        out_f = fl.filter_stripes(img, tile, no_cells, cells, None, 2500)
+        assert out_f.dtype == np.float64
+        assert np.abs(out_f - ref_f).max() / ref_f.max() < 1e-4
+    with pytest.raises(KeyError):
+        fl.filter_stripes(st[0], "99_20", no_cells, cells, _shadow(H, W, False), 2500)
+    bad = dict(shadow)
+    bad["darkfield"] = np.zeros((H - 1, W), np.uint16)
+    with pytest.raises(ValueError):
+        fl.filter_stripes(st[0], tile, no_cells, cells, bad, 2500)
+
+
+def test_filter_planes_equals_per_plane_calls_and_mixed_levels(production_configs):
+    no_cells, cells = production_configs
+    H, W = 256, 320
+    st = S.synthetic_stack(5, H, W, base_seed=21, cells_every=2)
+    shadow = _shadow(H, W)
+    batch = fl.filter_planes(st, "0_0", no_cells, cells, shadow, 2500)
+    for z in range(5):
+        one = fl.filter_stripes(st[z], "0_0", no_cells, cells, shadow, 2500)
+        np.testing.assert_array_equal(batch[z], one)
+    # configs with different decomposition depth are grouped by the dispatch decision
+    cells3 = dict(cells, level=3)
+    mixed = fl.filter_planes(st, "0_0", no_cells, cells3, shadow, 2500)
+    for z in range(5):
+        ref = OF.filter_stripes(st[z].astype(np.float32), "0_0", no_cells, cells3, shadow, 2500)
+        frac, mx, _ = u16_agreement(mixed[z], ref)
+        assert frac >= U16_FRACTION
+
+
+def test_execute_worker_matches_oracle_worker(production_configs):
+    no_cells, cells = production_configs
+    Z, H, W = 6, 200, 240
+    st = S.synthetic_stack(Z, H, W, base_seed=31, cells_every=3).astype(np.float32)
+    shadow = _shadow(H, W)
+    sink = np.zeros((1, 1, 10, H, W), dtype=np.uint16)  # dataset shorter than the chunk end -> clamp
+    ref_sink = np.zeros_like(sink)
+    args = dict(
+        batch_super_chunk=(slice(0, 12), slice(0, H), slice(0, W)),
+        batch_internal_slice=(slice(6, 12), slice(0, H), slice(0, W)),
+        cells_config=cells, no_cells_config=no_cells, overlap_prediction_chunksize=(0, 0, 0),
+        shadow_correction=shadow, dataset_name="0_0.zarr", logger=None,
+    )
+    zd.execute_worker(data=st[None], output_destriped_zarr=sink, **args)
+    OW.execute_worker(data=st[None], output_destriped_zarr=ref_sink, **args)
+    assert np.all(sink[0, 0, :6] == 0)
+    frac, mx, _ = u16_agreement(sink[0, 0, 6:10], ref_sink[0, 0, 6:10])
+    print(f"execute_worker: within+-1 {frac:.6f} max {mx}")
+    assert frac >= U16_FRACTION and sink[0, 0, 6:10].max() > 0
+
+
+def test_destripe_volume_streams_and_matches_chunk_call(production_configs):
+    no_cells, cells = production_configs
+    Z, H, W = 40, 160, 192
+    vol = S.synthetic_stack(Z, H, W, base_seed=41, cells_every=4, n_unique=8)
+    shadow = _shadow(H, W)
+    out = np.zeros((Z, H, W), np.uint16)
+    t = zd.destripe_volume(vol, out, no_cells, cells, shadow, chunk_planes=16)
+    assert t["planes"] == Z and t["wall_s"] > 0
+    ref = fl.filter_planes(vol, "0_0", no_cells, cells, shadow, 2500)
+    np.testing.assert_array_equal(out, ref)
+    # Z-slab of "rank 1 of 2" only touches its own planes
+    out2 = np.zeros((Z, H, W), np.uint16)
+    z0, z1 = zd.z_slab(Z, 1, 2, align=16)
+    zd.destripe_volume(vol, out2, no_cells, cells, shadow, chunk_planes=16, z_range=(z0, z1))
+    np.testing.assert_array_equal(out2[z0:z1], ref[z0:z1])
+    assert not out2[:z0].any()
+
+
+def test_error_paths():
+    eng = E.DestripeEngine(64, 80, max_planes=2)
+    p = E.make_params(dict(level=None, sigma=8, max_threshold=3))
+    with pytest.raises(ValueError):
+        eng.filter_chunk(np.zeros((1, 64, 81), np.uint16), p)
+    with pytest.raises(ValueError):  # shadow requested without flat/dark
+        eng.filter_chunk(np.zeros((1, 64, 80), np.uint16), p, flags=E.FLAG_SHADOW)
+    with pytest.raises(ValueError):
+        eng.set_flat_dark(np.ones((64, 81), np.float32), np.ones((64, 80), np.float32))
+    eng.close()
