@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the destripe hot path (BASELINE.json metric: destriped Mpixel/s of uint16 planes).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 engine (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+One "step" = one pass of the hot path over one synthetic 128 x 2048 x 2048 uint16 chunk
+(BASELINE.json configs[1]; `--workload c3` = dual-config dispatch + dark/flat epilogue,
+configs[2]).  Every rank owns its own chunk (weak scaling, Z-slab sharding, no collective).
+`value` is measured with the chunk resident in HBM (CUDA events on the engine's compute
+stream); `e2e` goes through the public API with pinned HOST buffers (H2D + D2H inside the
+timed region).  The chunk (1.07 GB in, 1.07 GB out) is far larger than the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NO_CELLS = {"wavelet": "db3", "level": None, "sigma": 128, "max_threshold": 12}  # run_capsule.py:377-382
+CELLS = {"wavelet": "db3", "level": None, "sigma": 64, "max_threshold": 3}  # run_capsule.py:383-388
+HIGH_INT = 2500  # zarr_destriper.py:326
+METRIC = "destriped Mpixel/s (uint16 planes)"
+ALGO_BYTES_PER_PX = 4.0  # uint16 in + uint16 out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--planes", type=int, default=128)
+    ap.add_argument("--height", type=int, default=2048)
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--batch-planes", type=int, default=0, help="planes per kernel launch (0 = engine default)")
+    ap.add_argument("--unique-planes", type=int, default=16)
+    ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU-baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    kind = (
+        "log-space filter (no_cells config: db3, level None, sigma 128, max_threshold 12)"
+        if args.workload == "c2"
+        else "dual-config dispatch (cells sigma 64/thr 3, no_cells sigma 128/thr 12) + dark/flat epilogue"
+    )
+    return f"synthetic Zarr chunk {args.planes}x{args.height}x{args.width} uint16, {kind}"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(workload):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fp:
+            return json.load(fp).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def cpu_reference_run(args, n_planes, cores, seed=1000):
+    """Time the oracle port of filter_stripes / log_space_fft_filtering on the host cores with the
+    reference's scheduling shape (N processes, whole blocks of planes each)."""
+    from aind_smartspim_destripe_b200 import synthetic as S
+    from oracle import worker as OW
+
+    stack = S.synthetic_stack(n_planes, args.height, args.width, base_seed=seed,
+                              cells_every=2 if args.workload == "c3" else 0)
+    shadow = None
+    cells = NO_CELLS
+    if args.workload == "c3":
+        flat, dark = S.synthetic_flat_dark(args.height, args.width)
+        shadow = dict(retrospective=True, flatfield=flat, darkfield=dark, tile_config=None)
+        cells = CELLS
+    t0 = time.perf_counter()
+    OW.run_planes_multiprocess(stack, NO_CELLS, cells, shadow, cores)
+    dt = time.perf_counter() - t0
+    return n_planes * args.height * args.width / dt / 1e6, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  pywt / skimage cannot be
+    installed here (no network), so the timed code is the oracle port (kind = "port")."""
+    from aind_smartspim_destripe_b200 import distributed as D
+    from oracle import worker as OW
+
+    rank, world, _ = D.env_rank()
+    if rank != 0:
+        return
+    cores = OW.get_cpu_limit()
+    n_planes = args.cpu_planes or cores
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_run(args, max(1, cores // 2), cores)
+    vals, times = [], []
+    for k in range(args.steps):
+        v, dt = cpu_reference_run(args, n_planes, cores, seed=2000 + 100 * k)
+        vals.append(v)
+        times.append(dt)
+    total_px = n_planes * args.height * args.width * args.steps
+    value = total_px / sum(times) / 1e6
+    sample = f"{n_planes} planes of {args.height}x{args.width} per step on {cores} processes (bounded sample of the workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "CPU path; oracle port of the reference (pywt/skimage not installable)"},
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+
+    from aind_smartspim_destripe_b200 import distributed as D
+    from aind_smartspim_destripe_b200 import engine as E
+    from aind_smartspim_destripe_b200 import synthetic as S
+
+    rank, world, local = D.init()
+    device = local if world > 1 else int(os.environ.get("DSTR_DEVICE", "0"))
+    torch.cuda.set_device(device)
+    Z, H, W = args.planes, args.height, args.width
+    px_per_step = Z * H * W
+
+    # ---- synthetic chunk (seeded; ranks get different planes) ---------------------------------
+    stack = S.synthetic_stack(Z, H, W, base_seed=10_000 * rank, n_unique=args.unique_planes,
+                              cells_every=2 if args.workload == "c3" else 0)
+    batch = args.batch_planes or min(Z, 128)
+    eng = E.DestripeEngine(H, W, max_planes=batch, device=device)
+    pn, pc = E.make_params(NO_CELLS), None
+    mode, flags = E.MODE_LOGSPACE, 0
+    if args.workload == "c3":
+        flat, dark = S.synthetic_flat_dark(H, W)
+        eng.set_flat_dark(flat, dark.astype(np.float32))
+        pc, mode, flags = E.make_params(CELLS), E.MODE_DISPATCH, E.FLAG_SHADOW
+
+    d_in = E.DeviceBuffer(eng, stack.nbytes)
+    d_out = E.DeviceBuffer(eng, stack.nbytes)
+    d_in.upload(stack)
+    stream = torch.cuda.ExternalStream(eng.compute_stream(), device=device)
+
+    def step_resident():
+        eng.filter_chunk_ptr(d_in.ptr, E.DSTR_U16, d_out.ptr, E.DSTR_U16, Z, pc, pn, HIGH_INT, mode,
+                             flags | E.FLAG_NO_SYNC)
+
+    # ---- HBM-resident timing (value) ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    eng.synchronize()
+    D.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
+    eng.reset_timers()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(stream)
+    eng.synchronize()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms_local = ev0.elapsed_time(ev1)
+    _, launches = eng.timers()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = D.max_over_ranks(ms_local)
+    value = world * px_per_step * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- per-stage device times (CUDA events on the compute stream, same steps) -----------------
+    eng.set_profiling(True)
+    eng.reset_timers()
+    for _ in range(args.steps):
+        eng.filter_chunk_ptr(d_in.ptr, E.DSTR_U16, d_out.ptr, E.DSTR_U16, Z, pc, pn, HIGH_INT, mode, flags)
+    stage_ms, _ = eng.timers()
+    eng.set_profiling(False)
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    dom = max((k for k in stage_ms if k != "chunk_total"), key=lambda k: stage_ms[k])
+    peak, peak_src = measured_peak()
+    algo_bytes = ALGO_BYTES_PER_PX * px_per_step
+    achieved = algo_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch_group": algo_bytes,
+        "whole_pipeline_frac": (algo_bytes / (ms_total / args.steps * 1e-3) / 1e9) / peak,
+        "stage_ms_per_step": stage_ms,
+    }
+
+    # ---- end to end through the public API with pinned host buffers ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin_in = E.PinnedBuffer((Z, H, W), np.uint16)
+        pin_out = E.PinnedBuffer((Z, H, W), np.uint16)
+        pin_in.array[...] = stack
+        for _ in range(2):
+            eng.filter_chunk(pin_in.array, pn, cells=pc, out=pin_out.array, high_int=HIGH_INT, mode=mode, flags=flags)
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.filter_chunk(pin_in.array, pn, cells=pc, out=pin_out.array, high_int=HIGH_INT, mode=mode, flags=flags)
+        dt = time.perf_counter() - t0
+        dt = D.max_over_ranks(dt)
+        # result check-sum read back on the host (the step's result is consumed)
+        checksum = int(pin_out.array[:: max(1, Z // 4), ::64, ::64].astype(np.int64).sum())
+        e2e = {"value": world * px_per_step * args.steps / dt / 1e6, "unit": "Mpixel/s",
+               "h2d_bytes_per_step": int(stack.nbytes), "d2h_bytes_per_step": int(stack.nbytes),
+               "ms_per_step": 1e3 * dt / args.steps, "checksum": checksum}
+        pin_in.free()
+        pin_out.free()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import worker as OW
+
+        cores = OW.get_cpu_limit()
+        n_planes = args.cpu_planes or 2 * cores
+        v, dt = cpu_reference_run(args, n_planes, cores)
+        cpu = {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+               "sample": f"{n_planes} planes of {H}x{W} on {cores} processes, {dt:.1f} s wall "
+                         "(oracle port; pywt/skimage not installable)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "planes_per_launch": batch,
+                       "l2_policy": "inputs (1.07 GB/chunk) larger than L2; no flush needed",
+                       "sharding": f"one chunk per rank, {world} rank(s), no collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    d_in.free()
+    d_out.free()
+    eng.close()
+    D.shutdown()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
