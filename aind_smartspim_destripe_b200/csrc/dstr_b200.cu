@@ -42,10 +42,16 @@ struct LevelGeom {
     size_t pstride;  // floats per plane
 };
 
+// Device tables of one (level, config): FIR taps and the rank-J cosine correction.
+struct NotchDevice {
+    float sigma = -1.f;  // sigma the tables were built for
+    double eps = -1.0;
+    float* d_buf = nullptr;  // one allocation: te | to | T1 | T2
+    NotchTables nt = {};
+};
+
 struct TapTable {
-    float sigma[2] = {-1.f, -1.f};  // [cells, no_cells] the table was built for
-    int ntap_pad = 0, u_lo = 0;
-    float* d_taps = nullptr;  // [2 cfg][2][ntap_pad]
+    NotchDevice cfg[2];  // [0] no_cells, [1] cells
 };
 
 struct TimerSpan {
@@ -77,6 +83,7 @@ struct dstr_ctx {
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     float fg_half_thr = 384.f;
+    double notch_eps = 1e-6;  // truncation tolerance of the hybrid notch operator (0 = dense)
     // instrumentation
     bool profiling = false;
     int debug_stop = DSTR_STAGE_NONE;
@@ -187,45 +194,202 @@ void notch_kernels_host(int n, double s, std::vector<double>& hp, std::vector<do
     }
 }
 
-int build_taps(dstr_ctx* ctx, int level, float sigma_cells, float sigma_nocells) {
-    TapTable& T = ctx->taps[level];
-    if (T.d_taps && T.sigma[0] == sigma_cells && T.sigma[1] == sigma_nocells) return 0;
-    const int n = ctx->geom[level].W;
-    const int Hl = ctx->geom[level].H;
-    const int ntap = n;  // full circular support (exact)
-    const int ntap_pad = (ntap + 7) & ~7;
-    const int u_lo = -(n / 2);
-    std::vector<float> host((size_t)4 * ntap_pad, 0.f);
-    const float sig[2] = {sigma_nocells, sigma_cells};  // cfg 0 = no_cells, cfg 1 = cells
-    for (int cfg = 0; cfg < 2; ++cfg) {
-        if (!(sig[cfg] > 0.f)) continue;  // unused configuration
-        // s = rows of this band * sigma / min(H, W)   (filtering.py:180,208-213)
-        const double wf = (double)sig[cfg] / (double)std::min(ctx->H, ctx->W);
-        const double s = (double)Hl * wf;
-        std::vector<double> hp, hq;
-        notch_kernels_host(n, s, hp, hq);
-        float* tp = host.data() + (size_t)cfg * 2 * ntap_pad;
-        float* tq = tp + ntap_pad;
-        for (int k = 0; k < ntap; ++k) {
-            int u = u_lo + k;
-            int m = ((u % n) + n) % n;
-            tp[k] = (float)hp[m];
-            tq[k] = (float)hq[m];
+// ---- hybrid design of the even-part operator -------------------------------------------------
+// a_j = w(2|j| - 1) (a_0 = 1) = G(j) + r(j):  G(j) = w(2 phi(j) - 1) with the smooth absolute
+// value phi(j) = j erf(j / beta) + beta / sqrt(pi) exp(-j^2 / beta^2); r is supported on the
+// lowest ~4.5 beta modes.  The kernel of G is compact (radius R_G), r is applied as a rank-J
+// cosine correction.  beta is chosen per band to minimise the work; tolerances are relative
+// to the L1 norm of the kernel (i.e. to the operator's gain on a bounded row).
+struct NotchHost {
+    std::vector<float> te, to, T1, T2;
+    int ntap_e = 0, ue_lo = 0, ntap_o = 0, uo_lo = 0, J = 0, Jpad = 0;
+};
+
+void idft_even(int n, const std::vector<double>& coef, const std::vector<double>& ct,
+               std::vector<double>& h) {
+    // h[u] = (1/n) [c_0 + 2 sum_{1<=j<n/2} c_j cos(2 pi j u / n) + (n even) c_{n/2} cos(pi u)]
+    const int J = (int)coef.size();
+    h.assign(n, 0.0);
+    for (int u = 0; u < n; ++u) {
+        double acc = 0.0;
+        long long idx = 0;
+        for (int j = 0; j < J; ++j) {
+            const double wt = (j == 0 || (n % 2 == 0 && j == n / 2)) ? 1.0 : 2.0;
+            acc += wt * coef[j] * ct[idx];
+            idx += u;
+            if (idx >= n) idx -= n;
+        }
+        h[u] = acc / n;
+    }
+}
+
+int tail_radius(int n, const std::vector<double>& h, double eps) {
+    // smallest R such that sum_{circular distance > R} |h| < eps * sum |h|
+    const int nh = n / 2;
+    double tot = 0.0;
+    for (double v : h) tot += std::fabs(v);
+    std::vector<double> ring(nh + 1, 0.0);
+    for (int u = 0; u < n; ++u) ring[std::min(u, n - u)] += std::fabs(h[u]);
+    double tail = 0.0;
+    int R = nh;
+    for (int d = nh; d >= 1; --d) {
+        tail += ring[d];
+        if (tail >= eps * tot) break;
+        R = d - 1;
+    }
+    return R;
+}
+
+void pack_taps(int n, const std::vector<double>& h, int R, bool dense, std::vector<float>& taps,
+               int& u_lo, int& ntap_pad) {
+    int ntap;
+    if (dense) {
+        u_lo = -(n / 2);
+        ntap = n;
+    } else {
+        u_lo = -R;
+        ntap = 2 * R + 1;
+    }
+    ntap_pad = (ntap + 7) & ~7;
+    taps.assign(ntap_pad, 0.f);
+    for (int k = 0; k < ntap; ++k) {
+        const int u = u_lo + k;
+        taps[k] = (float)h[((u % n) + n) % n];
+    }
+}
+
+void design_notch(int n, double s, double eps, NotchHost& out) {
+    const int nh = n / 2;
+    const int Jn = (n % 2 == 0) ? nh + 1 : (n + 1) / 2;  // cosine modes j = 0..Jn-1
+    auto w = [&](double k) { return std::exp(-(k * k) / (2.0 * s * s)); };
+    std::vector<double> ct(n);
+    for (int i = 0; i < n; ++i) ct[i] = std::cos(2.0 * M_PI * (double)i / (double)n);
+    std::vector<double> a(Jn), b(Jn);
+    for (int j = 0; j < Jn; ++j) {
+        a[j] = (j == 0) ? w(0) : w(2.0 * j - 1.0);
+        b[j] = w(2.0 * j);
+    }
+    if (n % 2 == 0) a[nh] = w(n - 1.0);
+    std::vector<double> hb;
+    idft_even(n, b, ct, hb);
+    const int nhp8 = (nh + 1 + 7) & ~7;
+    const int nhp4 = (nh + 4) & ~3;
+
+    // dense fallback: exact kernels of full circular length
+    std::vector<double> ha;
+    idft_even(n, a, ct, ha);
+    double best_cost = 2.0 * ((n + 7) & ~7);
+    bool hybrid = false;
+    double best_beta = 0.0;
+    int best_RG = 0, best_J = 0;
+    int Rb = nh;
+    std::vector<double> best_G, best_hG;
+    if (eps > 0.0 && n >= 48) {
+        Rb = tail_radius(n, hb, eps);
+        const double betas[] = {6, 8, 10, 12, 14, 16, 20, 24, 32};
+        for (double beta : betas) {
+            std::vector<double> G(Jn), hG;
+            for (int j = 0; j < Jn; ++j) {
+                const double x = (double)j;
+                const double phi = x * std::erf(x / beta) + beta / std::sqrt(M_PI) * std::exp(-(x / beta) * (x / beta));
+                G[j] = w(2.0 * phi - 1.0);
+            }
+            idft_even(n, G, ct, hG);
+            const int RG = tail_radius(n, hG, eps);
+            // number of low modes to keep: sum of dropped 2|r_j| below eps
+            double tail = 0.0;
+            int J = Jn;
+            for (int j = Jn - 1; j >= 0; --j) {
+                tail += 2.0 * std::fabs(a[j] - G[j]);
+                if (tail >= eps) break;
+                J = j;
+            }
+            if (2 * RG + 1 >= n || 2 * Rb + 1 >= n || J >= nh) continue;
+            const double cost = (double)(((2 * RG + 1 + 7) & ~7) + ((2 * Rb + 1 + 7) & ~7)) + 2.5 * J;
+            if (cost < best_cost) {
+                best_cost = cost;
+                hybrid = true;
+                best_beta = beta;
+                best_RG = RG;
+                best_J = J;
+                best_G = G;
+                best_hG = hG;
+            }
         }
     }
-    if (!T.d_taps || T.ntap_pad != ntap_pad) {
-        if (T.d_taps) cudaFree(T.d_taps);
-        T.d_taps = nullptr;
-        CK(ctx, cudaMalloc(&T.d_taps, host.size() * sizeof(float)));
+    (void)best_beta;
+    if (!hybrid) {
+        pack_taps(n, ha, 0, true, out.te, out.ue_lo, out.ntap_e);
+        pack_taps(n, hb, 0, true, out.to, out.uo_lo, out.ntap_o);
+        out.J = 0;
+        out.Jpad = 0;
+        out.T1.clear();
+        out.T2.clear();
+        return;
     }
-    CK(ctx, cudaMemcpyAsync(T.d_taps, host.data(), host.size() * sizeof(float),
-                            cudaMemcpyHostToDevice, ctx->s_comp));
+    pack_taps(n, best_hG, best_RG, false, out.te, out.ue_lo, out.ntap_e);
+    pack_taps(n, hb, Rb, false, out.to, out.uo_lo, out.ntap_o);
+    const int J = best_J;
+    out.J = J;
+    out.Jpad = (J + 31) & ~31;
+    out.T1.assign((size_t)nhp4 * out.Jpad, 0.f);
+    out.T2.assign((size_t)std::max(J, 1) * nhp8, 0.f);
+    for (int j = 0; j < J; ++j) {
+        const double r = a[j] - best_G[j];
+        const double rho = ((j == 0) ? 1.0 : 2.0) * r / n;  // J < n/2: no Nyquist mode here
+        for (int v = 0; v <= nh; ++v) {
+            const double omega = (v == 0 || (n % 2 == 0 && v == nh)) ? 1.0 : 2.0;
+            const double c = ct[(int)(((long long)j * v) % n)];
+            out.T1[(size_t)v * out.Jpad + j] = (float)(omega * c);
+            out.T2[(size_t)j * nhp8 + v] = (float)(rho * c);
+        }
+    }
+}
+
+int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
+    NotchDevice& D = ctx->taps[level].cfg[cfg];
+    if (D.d_buf && D.sigma == sigma && D.eps == ctx->notch_eps) return 0;
+    const int n = ctx->geom[level].W;
+    const int Hl = ctx->geom[level].H;
+    // s = rows of this band * sigma / min(H, W)   (filtering.py:180,208-213)
+    const double s = (double)Hl * ((double)sigma / (double)std::min(ctx->H, ctx->W));
+    NotchHost hst;
+    design_notch(n, s, ctx->notch_eps, hst);
+    auto pad4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
+    const size_t o_te = 0, o_to = o_te + pad4(hst.te.size()), o_T1 = o_to + pad4(hst.to.size()),
+                 o_T2 = o_T1 + pad4(hst.T1.size()), total = o_T2 + pad4(hst.T2.size());
+    std::vector<float> host(total, 0.f);
+    std::copy(hst.te.begin(), hst.te.end(), host.begin() + o_te);
+    std::copy(hst.to.begin(), hst.to.end(), host.begin() + o_to);
+    std::copy(hst.T1.begin(), hst.T1.end(), host.begin() + o_T1);
+    std::copy(hst.T2.begin(), hst.T2.end(), host.begin() + o_T2);
+    if (D.d_buf) {
+        CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+        cudaFree(D.d_buf);
+        D.d_buf = nullptr;
+    }
+    CK(ctx, cudaMalloc(&D.d_buf, total * sizeof(float)));
+    CK(ctx, cudaMemcpyAsync(D.d_buf, host.data(), total * sizeof(float), cudaMemcpyHostToDevice, ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
-    T.ntap_pad = ntap_pad;
-    T.u_lo = u_lo;
-    T.sigma[0] = sigma_cells;
-    T.sigma[1] = sigma_nocells;
+    D.nt.te = D.d_buf + o_te;
+    D.nt.to = D.d_buf + o_to;
+    D.nt.T1 = D.d_buf + o_T1;
+    D.nt.T2 = D.d_buf + o_T2;
+    D.nt.ntap_e = hst.ntap_e;
+    D.nt.ue_lo = hst.ue_lo;
+    D.nt.ntap_o = hst.ntap_o;
+    D.nt.uo_lo = hst.uo_lo;
+    D.nt.J = hst.J;
+    D.nt.Jpad = hst.Jpad;
+    D.sigma = sigma;
+    D.eps = ctx->notch_eps;
     return 0;
+}
+
+int build_taps(dstr_ctx* ctx, int level, float sigma_cells, float sigma_nocells) {
+    int rc = build_taps_cfg(ctx, level, 0, sigma_nocells);
+    if (rc) return rc;
+    return build_taps_cfg(ctx, level, 1, sigma_cells);
 }
 
 cudaEvent_t get_event(dstr_ctx* ctx) {
@@ -374,15 +538,19 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
                 fa.pstride = g.pstride;
                 fa.lstat = ctx->d_lstat + (size_t)(l - 1) * level_stride;
                 fa.stat_stride = stat_stride;
-                fa.taps = T.d_taps;
-                fa.ntap_pad = T.ntap_pad;
-                fa.u_lo = T.u_lo;
+                fa.nt[0] = T.cfg[0].nt;
+                fa.nt[1] = T.cfg[1].nt;
+                fa.nh = g.W / 2;
+                fa.nhp8 = (fa.nh + 1 + 7) & ~7;
                 fa.n_pad8 = (g.W + 7) & ~7;
-                const int xlen_log = fa.n_pad8 + fa.ntap_pad;
-                fa.xlen_phys = xlen_log / 8 * 9;
-                const size_t smem = sizeof(float) * ((size_t)2 * fa.ntap_pad +
-                                                     (size_t)2 * FR_ROWS * fa.xlen_phys +
-                                                     (size_t)FR_ROWS * fa.n_pad8) +
+                fa.ntap_e_max = std::max(fa.nt[0].ntap_e, fa.nt[1].ntap_e);
+                fa.ntap_o_max = std::max(fa.nt[0].ntap_o, fa.nt[1].ntap_o);
+                fa.Jpad_max = std::max(fa.nt[0].Jpad, fa.nt[1].Jpad);
+                fa.xlen_e_phys = (fa.nhp8 + fa.ntap_e_max) / 8 * 9;
+                fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
+                const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
+                                                     (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
+                                                     (size_t)FR_ROWS * fa.n_pad8 + (size_t)FR_ROWS * fa.Jpad_max) +
                                     (size_t)FR_ROWS * fa.n_pad8;
                 if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
                 const int epl = (g.W + 31) / 32;
@@ -577,7 +745,8 @@ int dstr_destroy(dstr_ctx* ctx) {
     for (int l = 0; l <= kMaxLevels; ++l) {
         if (ctx->d_A[l]) cudaFree(ctx->d_A[l]);
         if (ctx->d_H[l]) cudaFree(ctx->d_H[l]);
-        if (ctx->taps[l].d_taps) cudaFree(ctx->taps[l].d_taps);
+        for (int c = 0; c < 2; ++c)
+            if (ctx->taps[l].cfg[c].d_buf) cudaFree(ctx->taps[l].cfg[c].d_buf);
     }
     if (ctx->d_lstat) cudaFree(ctx->d_lstat);
     if (ctx->d_pstat) cudaFree(ctx->d_pstat);
@@ -895,6 +1064,54 @@ int dstr_set_debug_stop(dstr_ctx* ctx, int stage) {
     ctx->debug_stop = stage;
     return 0;
 }
+int dstr_set_notch_tolerance(dstr_ctx* ctx, double eps) {
+    if (!ctx || !(eps >= 0.0) || eps > 1e-2) return DSTR_E_ARG;
+    ctx->notch_eps = eps;
+    return 0;
+}
+
+int dstr_notch_design(int n, double s, double eps, int* info /*[6]*/) {
+    if (n <= 0 || !(s > 0.0) || !info) return DSTR_E_ARG;
+    NotchHost h;
+    design_notch(n, s, eps, h);
+    info[0] = h.ntap_e;
+    info[1] = h.ue_lo;
+    info[2] = h.ntap_o;
+    info[3] = h.uo_lo;
+    info[4] = h.J;
+    info[5] = h.Jpad;
+    return 0;
+}
+
+int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* y) {
+    // y = B x evaluated on the host with exactly the tables the device uses (float32 taps,
+    // double accumulation): lets CPU tests bound the truncation error of the hybrid design.
+    if (n <= 0 || !(s > 0.0) || !x || !y) return DSTR_E_ARG;
+    NotchHost h;
+    design_notch(n, s, eps, h);
+    const int nh = n / 2;
+    const int nhp8 = (nh + 1 + 7) & ~7;
+    std::vector<double> xe(n), xo(n);
+    for (int t = 0; t < n; ++t) {
+        const int tr = (t == 0) ? 0 : n - t;
+        xe[t] = 0.5 * (x[t] + x[tr]);
+        xo[t] = 0.5 * (x[t] - x[tr]);
+    }
+    std::vector<double> c(std::max(h.J, 1), 0.0);
+    for (int j = 0; j < h.J; ++j)
+        for (int v = 0; v <= nh; ++v) c[j] += (double)h.T1[(size_t)v * h.Jpad + j] * xe[v];
+    for (int t = 0; t <= nh; ++t) {
+        double ye = 0.0, yo = 0.0;
+        for (int k = 0; k < h.ntap_e; ++k) ye += (double)h.te[k] * xe[(((t - (h.ue_lo + k)) % n) + n) % n];
+        for (int k = 0; k < h.ntap_o; ++k) yo += (double)h.to[k] * xo[(((t - (h.uo_lo + k)) % n) + n) % n];
+        for (int j = 0; j < h.J; ++j) ye += c[j] * (double)h.T2[(size_t)j * nhp8 + t];
+        y[t] = ye + yo;
+        const int tm = n - t;
+        if (t != 0 && tm != t) y[tm] = ye - yo;
+    }
+    return 0;
+}
+
 int dstr_set_subchunk(dstr_ctx* ctx, int planes) {
     if (!ctx || planes < 0) return DSTR_E_ARG;
     ctx->subchunk = planes;

@@ -450,11 +450,22 @@ otsu_kernel(LevelStat* __restrict__ lstat_base, size_t level_stride, int stat_st
 // =============================================================================================
 // Row filter.  For every row of cH_l (filtering.py:195-217):
 //   m = sqrt(c*c) > thr;  bg = m ? 0 : c;  med = median(bg);  x = m ? med : c
-//   bgf = irfft(rfft(x) * g) = x - B x,  B[t][v] = hp[(t-v) mod n] + hq[(t+v) mod n]  (exact)
+//   bgf = irfft(rfft(x) * g) = x - B x      (g on the PACKED rfft index, scipy.fftpack layout)
 //   cH' = m ? c : bgf   =>   dH = cH' - c = m ? 0 : -(B x)[t]
-// One warp per row for the selection; the whole block for the register-tiled FIR.
-// Shared rows are stored with one pad word per 8 (phys = a + (a >> 3)) so that lanes reading
-// windows 8 apart hit distinct banks.
+//
+// B in the time domain.  With x_e / x_o the circularly even / odd parts of x about index 0,
+//   B x = A x_e + Bo x_o,  A: cosine multipliers a_j = w(2j-1) (a_0 = 1),  Bo: sine multipliers
+//   b_j = w(2j),  w(k) = exp(-k^2 / 2 s^2).
+// Bo is a plain periodic Gaussian: a compact FIR `to`.  a_j has a kink at j = 0 (|2j| - 1), so
+// its kernel has 1/u^2 tails; it is split on the host (double precision) into a smooth part G
+// (compact FIR `te`) plus a remainder supported on the J lowest cosine modes, applied as a
+// rank-J correction:  c_j = sum_v T1[v][j] x_e[v],  y_e[t] += sum_j c_j T2[j][t].
+// Small bands use the dense kernels (J = 0, te / to of full circular length).  Both forms are
+// evaluated on the half range t = 0..n/2 and mirrored:  y[t] = y_e + y_o,  y[n-t] = y_e - y_o.
+//
+// One warp per row for selection / in-painting / the c_j; the whole block for the register-tiled
+// FIR.  FIR operands are stored with one pad word per 8 (phys = a + (a >> 3)) so that lanes whose
+// 8-output windows are 8 apart hit distinct banks.
 // =============================================================================================
 constexpr int FR_ROWS = 4;
 constexpr int FR_THREADS = 32 * FR_ROWS;
@@ -468,15 +479,15 @@ __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float(b);
 }
 
-// acc[i] += sum_k taps[k] * Xlog[8*m0 + i - k],  k = 0..ntap_pad-1 (ntap_pad % 8 == 0)
+// acc[i] += sum_k taps[k] * Xlog[8*m0 + i - k],  k = 0..ntap-1 (ntap % 8 == 0)
 __device__ __forceinline__ void fir8(float (&acc)[8], const float* __restrict__ Xphys,
-                                     const float* __restrict__ taps, int ntap_pad, int m0) {
+                                     const float* __restrict__ taps, int ntap, int m0) {
     const float* Xp = Xphys + 9 * m0;
     float w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = Xp[i];
     const float4* t4 = reinterpret_cast<const float4*>(taps);
-    for (int kk = 0; kk < ntap_pad / 8; ++kk) {
+    for (int kk = 0; kk < ntap / 8; ++kk) {
         const float4 ta = t4[2 * kk], tb = t4[2 * kk + 1];
         const float tk[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
         Xp -= 9;
@@ -489,17 +500,26 @@ __device__ __forceinline__ void fir8(float (&acc)[8], const float* __restrict__ 
     }
 }
 
+struct NotchTables {
+    const float* te;  // even-part FIR taps [ntap_e]; tap k <-> circular offset u = ue_lo + k
+    const float* to;  // odd-part FIR taps  [ntap_o]; tap k <-> u = uo_lo + k
+    const float* T1;  // [nhp4][Jpad]  omega_v cos(2 pi j v / n)   (v-major)
+    const float* T2;  // [J][nhp8]     rho_j   cos(2 pi j t / n)   (j-major)
+    int ntap_e, ue_lo, ntap_o, uo_lo, J, Jpad;
+};
+
 struct FilterLevelArgs {
     float* cH;
     int Hl, Wl, pitch;
     size_t pstride;
     const LevelStat* lstat;
     int stat_stride;
-    const float* taps;  // [2 cfg][2 (p,q)][ntap_pad]
-    int ntap_pad;       // multiple of 8
-    int u_lo;           // first tap offset
-    int xlen_phys;      // physical floats per X array
+    NotchTables nt[2];  // [0] no_cells, [1] cells
+    int nh;             // n / 2: the half range is t = 0..nh
+    int nhp8;           // nh + 1 rounded up to a multiple of 8
     int n_pad8;
+    int xlen_e_phys, xlen_o_phys;  // per-row physical floats (max over the two configs)
+    int ntap_e_max, ntap_o_max, Jpad_max;
 };
 
 template <int EPL>
@@ -507,28 +527,28 @@ __global__ void __launch_bounds__(FR_THREADS)
 filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.Wl;
-    const int ntap = a.ntap_pad;
-    float* s_tp = reinterpret_cast<float*>(smem_raw);  // [ntap]
-    float* s_tq = s_tp + ntap;                         // [ntap]
-    float* s_X = s_tq + ntap;                          // [FR_ROWS][xlen_phys]
-    float* s_XR = s_X + FR_ROWS * a.xlen_phys;         // [FR_ROWS][xlen_phys]
-    float* s_x = s_XR + FR_ROWS * a.xlen_phys;         // [FR_ROWS][n_pad8]
-    unsigned char* s_m = reinterpret_cast<unsigned char*>(s_x + FR_ROWS * a.n_pad8);  // [FR_ROWS][n_pad8]
+    float* s_te = reinterpret_cast<float*>(smem_raw);                 // [ntap_e_max]
+    float* s_to = s_te + a.ntap_e_max;                                // [ntap_o_max]
+    float* s_E = s_to + a.ntap_o_max;                                 // [FR_ROWS][xlen_e_phys]
+    float* s_O = s_E + FR_ROWS * a.xlen_e_phys;                       // [FR_ROWS][xlen_o_phys]
+    float* s_x = s_O + FR_ROWS * a.xlen_o_phys;                       // [FR_ROWS][n_pad8]
+    float* s_c = s_x + FR_ROWS * a.n_pad8;                            // [FR_ROWS][Jpad_max]
+    unsigned char* s_m = reinterpret_cast<unsigned char*>(s_c + FR_ROWS * a.Jpad_max);  // [FR_ROWS][n_pad8]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int z = blockIdx.y;
     const int row0 = blockIdx.x * FR_ROWS;
     const int nrows = min(FR_ROWS, a.Hl - row0);
     const int cfg = plane_uses_cells(pstat[z], dp);
+    const NotchTables nt = cfg ? a.nt[1] : a.nt[0];
     const float thr = a.lstat[(size_t)z * a.stat_stride].thr;
+    const int nh = a.nh;
 
-    {
-        const float* tsrc = a.taps + (size_t)cfg * 2 * ntap;
-        for (int i = tid; i < 2 * ntap; i += FR_THREADS) s_tp[i] = tsrc[i];
-    }
+    for (int i = tid; i < nt.ntap_e; i += FR_THREADS) s_te[i] = nt.te[i];
+    for (int i = tid; i < nt.ntap_o; i += FR_THREADS) s_to[i] = nt.to[i];
 
-    float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
     if (wid < nrows) {
+        float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
         // ---- load, mask, keys ------------------------------------------------------------
         unsigned key[EPL];
         float* xs = s_x + wid * a.n_pad8;
@@ -577,39 +597,111 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
         for (int e = lane; e < n; e += 32)
             if (ms[e]) xs[e] = med;
         __syncwarp();
-        // ---- circularly extended copies: X[a] = x[(a-OFF) mod n], XR[a] = x[(OFF-a) mod n] ---
-        const int OFF = a.u_lo + ntap;
-        const int xlen_log = a.n_pad8 + ntap;
-        float* X = s_X + wid * a.xlen_phys;
-        float* XR = s_XR + wid * a.xlen_phys;
-        for (int al = lane; al < xlen_log; al += 32) {
-            int t = (al - OFF) % n;
+        // ---- even / odd parts, circularly extended:  E[a] = x_e[(a - OFFe) mod n] ----------
+        float* E = s_E + wid * a.xlen_e_phys;
+        float* O = s_O + wid * a.xlen_o_phys;
+        {
+            const int OFF = nt.ue_lo + nt.ntap_e;
+            const int xlen_log = a.nhp8 + nt.ntap_e;
+            int t = (lane - OFF) % n;
             if (t < 0) t += n;
-            const int tr = (t == 0) ? 0 : n - t;
-            const int ph = al + (al >> 3);
-            X[ph] = xs[t];
-            XR[ph] = xs[tr];
+            const int step = 32 % n;
+            for (int al = lane; al < xlen_log; al += 32) {
+                const int tr = (t == 0) ? 0 : n - t;
+                E[al + (al >> 3)] = 0.5f * (xs[t] + xs[tr]);
+                t += step;
+                if (t >= n) t -= n;
+            }
+        }
+        {
+            const int OFF = nt.uo_lo + nt.ntap_o;
+            const int xlen_log = a.nhp8 + nt.ntap_o;
+            int t = (lane - OFF) % n;
+            if (t < 0) t += n;
+            const int step = 32 % n;
+            for (int al = lane; al < xlen_log; al += 32) {
+                const int tr = (t == 0) ? 0 : n - t;
+                O[al + (al >> 3)] = 0.5f * (xs[t] - xs[tr]);
+                t += step;
+                if (t >= n) t -= n;
+            }
+        }
+        __syncwarp();
+        // ---- rank-J correction coefficients  c_j = sum_v T1[v][j] x_e[v] ---------------------
+        if (nt.J > 0) {
+            const int OFF = nt.ue_lo + nt.ntap_e;
+            const int nhp4 = (nh + 4) & ~3;
+            for (int v = lane; v < nhp4; v += 32) {
+                const int al = v + OFF;
+                xs[v] = (v <= nh) ? E[al + (al >> 3)] : 0.f;
+            }
+            __syncwarp();
+            const float4* x4 = reinterpret_cast<const float4*>(xs);
+            const int Jpad = nt.Jpad;
+            float* cp = s_c + wid * a.Jpad_max;
+            for (int j0 = 0; j0 < Jpad; j0 += 64) {
+                const bool two = (j0 + 32) < Jpad;
+                const float* t1 = nt.T1 + j0 + lane;
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int v4 = 0; v4 < (nhp4 >> 2); ++v4) {
+                    const float4 xv = x4[v4];
+                    const float* tt = t1 + (size_t)(4 * v4) * Jpad;
+                    acc0 = fmaf(xv.x, __ldg(tt), acc0);
+                    acc0 = fmaf(xv.y, __ldg(tt + Jpad), acc0);
+                    acc0 = fmaf(xv.z, __ldg(tt + 2 * Jpad), acc0);
+                    acc0 = fmaf(xv.w, __ldg(tt + 3 * Jpad), acc0);
+                    if (two) {
+                        acc1 = fmaf(xv.x, __ldg(tt + 32), acc1);
+                        acc1 = fmaf(xv.y, __ldg(tt + Jpad + 32), acc1);
+                        acc1 = fmaf(xv.z, __ldg(tt + 2 * Jpad + 32), acc1);
+                        acc1 = fmaf(xv.w, __ldg(tt + 3 * Jpad + 32), acc1);
+                    }
+                }
+                cp[j0 + lane] = acc0;
+                if (two) cp[j0 + 32 + lane] = acc1;
+            }
         }
     }
     __syncthreads();
 
-    // ---- register-tiled FIR over (row, 8-output segment) pairs ---------------------------------
-    const int nseg = a.n_pad8 >> 3;
+    // ---- register-tiled FIRs + rank-J correction over (row, 8-output segment) pairs -----------
+    const int nseg = a.nhp8 >> 3;
     for (int w = tid; w < nrows * nseg; w += FR_THREADS) {
         const int r = w / nseg;
         const int seg = w - r * nseg;
-        float acc[8];
+        float ye[8], yo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        const int m0 = seg + (ntap >> 3);
-        fir8(acc, s_X + r * a.xlen_phys, s_tp, ntap, m0);
-        fir8(acc, s_XR + r * a.xlen_phys, s_tq, ntap, m0);
+        for (int i = 0; i < 8; ++i) ye[i] = yo[i] = 0.f;
+        fir8(ye, s_E + r * a.xlen_e_phys, s_te, nt.ntap_e, seg + (nt.ntap_e >> 3));
+        fir8(yo, s_O + r * a.xlen_o_phys, s_to, nt.ntap_o, seg + (nt.ntap_o >> 3));
+        if (nt.J > 0) {
+            const float* cp = s_c + r * a.Jpad_max;
+            const float4* t2 = reinterpret_cast<const float4*>(nt.T2 + 8 * seg);
+            const int stride4 = a.nhp8 >> 2;
+            for (int j = 0; j < nt.J; ++j) {
+                const float c = cp[j];
+                const float4 u0 = __ldg(t2 + (size_t)j * stride4);
+                const float4 u1 = __ldg(t2 + (size_t)j * stride4 + 1);
+                ye[0] = fmaf(c, u0.x, ye[0]);
+                ye[1] = fmaf(c, u0.y, ye[1]);
+                ye[2] = fmaf(c, u0.z, ye[2]);
+                ye[3] = fmaf(c, u0.w, ye[3]);
+                ye[4] = fmaf(c, u1.x, ye[4]);
+                ye[5] = fmaf(c, u1.y, ye[5]);
+                ye[6] = fmaf(c, u1.z, ye[6]);
+                ye[7] = fmaf(c, u1.w, ye[7]);
+            }
+        }
         float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + r) * a.pitch;
         const unsigned char* ms = s_m + r * a.n_pad8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int t = 8 * seg + i;
-            if (t < n) orow[t] = ms[t] ? 0.f : -acc[i];
+            if (t <= nh) {
+                orow[t] = ms[t] ? 0.f : -(ye[i] + yo[i]);
+                const int tm = n - t;
+                if (t != 0 && tm != t) orow[tm] = ms[tm] ? 0.f : -(ye[i] - yo[i]);
+            }
         }
     }
 }

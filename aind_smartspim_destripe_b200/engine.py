@@ -82,6 +82,9 @@ def load_library() -> C.CDLL:
             "dstr_level_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
             "dstr_foreground_threshold": (C.c_float, [C.c_float]),
             "dstr_notch_kernels": (C.c_int, [C.c_int, C.c_double, dp, dp]),
+            "dstr_notch_design": (C.c_int, [C.c_int, C.c_double, C.c_double, ip]),
+            "dstr_notch_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp]),
+            "dstr_set_notch_tolerance": (C.c_int, [vp, C.c_double]),
             "dstr_host_alloc": (C.c_int, [C.POINTER(vp), C.c_uint64]),
             "dstr_host_free": (C.c_int, [vp]),
             "dstr_host_register": (C.c_int, [vp, C.c_uint64]),
@@ -110,7 +113,7 @@ def load_library() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "dstr_create dstr_destroy dstr_last_error dstr_set_flat_dark dstr_filter_chunk dstr_plane_stats "
     "dstr_flatfield_correction dstr_max_level dstr_level_shape dstr_foreground_threshold "
-    "dstr_notch_kernels dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
+    "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
     "dstr_debug_fetch dstr_set_subchunk"
@@ -150,6 +153,25 @@ def notch_kernels(n: int, s: float) -> Tuple[np.ndarray, np.ndarray]:
     if rc:
         _raise(rc, None, "dstr_notch_kernels")
     return hp, hq
+
+
+def notch_design(n: int, s: float, eps: float = 1e-6) -> dict:
+    info = (C.c_int * 6)()
+    rc = load_library().dstr_notch_design(int(n), float(s), float(eps), info)
+    if rc:
+        _raise(rc, None, "dstr_notch_design")
+    return dict(zip(("ntap_e", "ue_lo", "ntap_o", "uo_lo", "J", "Jpad"), [int(v) for v in info]))
+
+
+def notch_apply_host(x: np.ndarray, s: float, eps: float = 1e-6) -> np.ndarray:
+    """B x from the device's own float32 tables (host evaluation, double accumulation)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    rc = load_library().dstr_notch_apply_host(x.size, float(s), float(eps), x.ctypes.data_as(dp), y.ctypes.data_as(dp))
+    if rc:
+        _raise(rc, None, "dstr_notch_apply_host")
+    return y
 
 
 def foreground_threshold(threshold_mask: float = 0.3) -> float:
@@ -379,6 +401,9 @@ class DestripeEngine:
 
     def set_subchunk(self, planes: int):
         self._ck(self.lib.dstr_set_subchunk(self.ctx, int(planes)), "dstr_set_subchunk")
+
+    def set_notch_tolerance(self, eps: float):
+        self._ck(self.lib.dstr_set_notch_tolerance(self.ctx, float(eps)), "dstr_set_notch_tolerance")
 
     def set_debug_stop(self, stage: int):
         self._ck(self.lib.dstr_set_debug_stop(self.ctx, int(stage)), "dstr_set_debug_stop")

@@ -122,6 +122,15 @@ float dstr_foreground_threshold(float threshold_mask);
  * Writes n doubles to each of hp, hq. */
 int dstr_notch_kernels(int n, double s, double* hp, double* hq);
 
+/* The device evaluates B x as A x_e + Bo x_o (even / odd parts of the row): a compact FIR for
+ * the smooth part of each plus a rank-J cosine correction for the kink of the packed layout;
+ * eps is the truncation tolerance relative to the operator gain (0 = dense, exact kernels).
+ * dstr_notch_design reports {ntap_e, ue_lo, ntap_o, uo_lo, J, Jpad}; dstr_notch_apply_host
+ * evaluates y = B x on the host from exactly the float32 tables the device uses. */
+int dstr_notch_design(int n, double s, double eps, int* info /*[6]*/);
+int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* y);
+int dstr_set_notch_tolerance(dstr_ctx* ctx, double eps);
+
 /* ---- pinned host memory ---------------------------------------------------------------------- */
 int dstr_host_alloc(void** ptr, uint64_t bytes);
 int dstr_host_free(void* ptr);

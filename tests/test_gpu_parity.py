@@ -86,6 +86,26 @@ def test_row_filter_matches_oracle_on_device_coefficients(shape, sigma):
     eng.close()
 
 
+def test_dense_and_hybrid_notch_agree():
+    """eps = 0 selects the dense (exact) kernels on every level; the default hybrid form must
+    agree with it far inside the 1e-4 intermediate tolerance."""
+    shape = (1600, 2000)
+    img = _plane(shape, seed=6)
+    eng = E.DestripeEngine(shape[0], shape[1], max_planes=2)
+    p = E.make_params(dict(level=None, sigma=128, max_threshold=12))
+    eng.set_debug_stop(E.STAGE_FILTER)
+    eng.filter_chunk(img[None], p, out_dtype=np.float32)
+    hyb = [eng.debug_fetch(E.FETCH_CH, l, 1)[0] for l in range(1, eng.max_level + 1)]
+    eng.set_notch_tolerance(0.0)
+    eng.filter_chunk(img[None], p, out_dtype=np.float32)
+    for l in range(1, eng.max_level + 1):
+        dense = eng.debug_fetch(E.FETCH_CH, l, 1)[0]
+        err = np.abs(hyb[l - 1] - dense).max() / max(np.abs(dense).max(), 1e-30)
+        print(f"level {l}: hybrid vs dense dH rel {err:.2e}")
+        assert err < 1e-4
+    eng.close()
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("cfg", ["no_cells", "cells"])
 def test_end_to_end_logspace_uint16(shape, cfg, production_configs):

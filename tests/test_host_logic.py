@@ -55,6 +55,32 @@ def test_notch_kernels_reproduce_packed_rfft_operator(n, s):
     np.testing.assert_allclose(x - B @ x, fftpack.irfft(fftpack.rfft(x) * g), atol=1e-12)
 
 
+@pytest.mark.parametrize("n,s", [(1026, 64.125), (1026, 32.06), (1002, 64.16), (503, 32.24), (254, 16.3), (129, 8.3),
+                                 (67, 4.3), (36, 2.25), (12, 0.75), (2050, 128.1)])
+@pytest.mark.parametrize("eps", [1e-6, 0.0])
+def test_device_notch_tables_bound_the_truncation_error(n, s, eps):
+    """The even/odd FIR + rank-J tables the device uses (host evaluation of the same float32
+    tables) reproduce irfft(rfft(x) * g) within the design tolerance, for hybrid and dense forms."""
+    d = E.notch_design(n, s, eps)
+    if eps == 0.0:
+        assert d["J"] == 0 and d["ntap_e"] >= n
+    g = fl.notch(n, s)
+    rng = np.random.default_rng(n)
+    for trial in range(3):
+        x = rng.standard_normal(n) if trial < 2 else np.ones(n)
+        if trial == 1:
+            x = np.cumsum(x) / 10.0
+        ref = x - fftpack.irfft(fftpack.rfft(x) * g)
+        y = E.notch_apply_host(x, s, eps)
+        assert np.abs(y - ref).max() <= (2e-6 if eps > 0 else 1e-7) * np.abs(x).max()
+
+
+def test_hybrid_design_is_much_cheaper_than_dense_on_production_bands():
+    for n, s in [(1026, 64.125), (1002, 64.16), (515, 32.19), (503, 32.24)]:
+        d = E.notch_design(n, s, 1e-6)
+        assert d["J"] > 0 and d["ntap_e"] + d["ntap_o"] + 2 * d["J"] < 0.4 * n
+
+
 def test_foreground_threshold_matches_float16_rule():
     thr = E.foreground_threshold(0.3)
     bits = np.arange(0, 0x7C00, dtype=np.uint16)  # all finite non-negative float16
