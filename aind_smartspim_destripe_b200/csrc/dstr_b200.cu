@@ -477,23 +477,28 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
         ScopedTimer t(ctx, l == 1 ? 0 : 1);
         const LevelGeom& gs = ctx->geom[l - 1];
         const LevelGeom& go = ctx->geom[l];
-        dim3 grid((go.W + AN_TOX - 1) / AN_TOX, (go.H + AN_TOY - 1) / AN_TOY, z);
+        const int cols_per_block = AN_OXW * AN_WARPS;
+        dim3 grid((go.W + cols_per_block - 1) / cols_per_block, (go.H + AN_TOY - 1) / AN_TOY, z);
         LevelStat* ls = ctx->d_lstat + (size_t)(l - 1) * level_stride;
+        const bool stats = dp.mode == 1;
+#define LAUNCH_AN1(IN_T, ST)                                                                          \
+    analysis_kernel<IN_T, true, ST><<<grid, AN_THREADS, 0, st>>>(                                      \
+        (const IN_T*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W, go.pitch,     \
+        go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr)
         if (l == 1) {
             if (in_dtype == DSTR_U16) {
-                analysis_kernel<uint16_t, true><<<grid, AN_THREADS, 0, st>>>(
-                    (const uint16_t*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H,
-                    go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+                if (stats) LAUNCH_AN1(uint16_t, true);
+                else LAUNCH_AN1(uint16_t, false);
             } else {
-                analysis_kernel<float, true><<<grid, AN_THREADS, 0, st>>>(
-                    (const float*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W,
-                    go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+                if (stats) LAUNCH_AN1(float, true);
+                else LAUNCH_AN1(float, false);
             }
         } else {
-            analysis_kernel<float, false><<<grid, AN_THREADS, 0, st>>>(
+            analysis_kernel<float, false, false><<<grid, AN_THREADS, 0, st>>>(
                 ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H,
                 go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
         }
+#undef LAUNCH_AN1
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -574,7 +579,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
             for (int l = L; l >= 2; --l) {
                 const LevelGeom& g = ctx->geom[l];
                 const LevelGeom& go = ctx->geom[l - 1];
-                dim3 grid((go.W + SY_TX - 1) / SY_TX, (go.H + SY_TY - 1) / SY_TY, z);
+                dim3 grid((go.W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (go.H + SY_TY - 1) / SY_TY, z);
                 const float* dA = (l == L) ? nullptr : ctx->d_A[l];
                 synth_kernel<false, float, float><<<grid, SY_THREADS, 0, st>>>(
                     dA, ctx->d_H[l], g.H, g.W, g.pitch, g.pstride, ctx->d_A[l - 1], go.H, go.W,
@@ -597,7 +602,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
         const LevelGeom& g = ctx->geom[L > 0 ? 1 : 0];
         const float* dA = (L >= 2) ? ctx->d_A[1] : nullptr;
         const float* dH = (L >= 1) ? ctx->d_H[1] : nullptr;
-        dim3 grid((W + SY_TX - 1) / SY_TX, (H + SY_TY - 1) / SY_TY, z);
+        dim3 grid((W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (H + SY_TY - 1) / SY_TY, z);
         const size_t ps = (size_t)H * W;
 #define LAUNCH_FINAL(IN_T, OUT_T)                                                                   \
     synth_kernel<true, IN_T, OUT_T><<<grid, SY_THREADS, 0, st>>>(                                   \

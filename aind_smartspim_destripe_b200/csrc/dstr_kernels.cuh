@@ -111,128 +111,185 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// aligned two-element loads / stores (caller guarantees alignment)
+__device__ __forceinline__ void load_pair(const unsigned short* p, float& a, float& b) {
+    const unsigned u = *reinterpret_cast<const unsigned*>(p);
+    a = (float)(u & 0xffffu);
+    b = (float)(u >> 16);
+}
+__device__ __forceinline__ void load_pair(const float* p, float& a, float& b) {
+    const float2 f = *reinterpret_cast<const float2*>(p);
+    a = f.x;
+    b = f.y;
+}
+__device__ __forceinline__ void store_pair(unsigned short* p, float a, float b) {
+    *reinterpret_cast<unsigned*>(p) = (unsigned)(unsigned short)a | ((unsigned)(unsigned short)b << 16);
+}
+__device__ __forceinline__ void store_pair(float* p, float a, float b) {
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+
 // =============================================================================================
 // analysis: one 2-D db3 level, symmetric mode, axis -2 first then axis -1 (pywt.dwt2), keeping
 // cA ('aa') and cH ('da': high-pass along Y, low-pass along X).
+//
+// Register-tiled, no shared-memory staging: one warp owns a strip of 30 output columns x
+// AN_TOY output rows.  Lane l holds input columns (2p, 2p+1), p = ox0 - 2 + l, and marches down
+// the rows with a 6-row sliding window (axis -2 pass: 24 FMA per output row); the axis -1 pass
+// takes the two neighbouring column pairs from lanes l-1 and l-2 by shuffle (8 SHFL + 12 FMA),
+// so lanes 2..31 emit outputs ox0 .. ox0+29.  Halo cost: 4 extra input rows per 2*AN_TOY and
+// 2 of 32 lanes.
 // =============================================================================================
-constexpr int AN_TOX = 64;
 constexpr int AN_TOY = 16;
-constexpr int AN_INW = 2 * AN_TOX + 4;  // 132
-constexpr int AN_INH = 2 * AN_TOY + 4;  // 36
-constexpr int AN_THREADS = 256;
+constexpr int AN_OXW = 30;  // output columns per warp
+constexpr int AN_WARPS = 8;
+constexpr int AN_THREADS = 32 * AN_WARPS;
 
-template <typename IN_T, bool FIRST>
+#ifdef DSTR_FAST_LOG
+#define DSTR_LOGF(x) __logf(x)
+#else
+#define DSTR_LOGF(x) logf(x)
+#endif
+
+template <typename IN_T, bool FIRST, bool STATS>
 __global__ void __launch_bounds__(AN_THREADS)
 analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_t in_pstride,
                 float* __restrict__ cA, float* __restrict__ cH, int Ho, int Wo, int out_pitch,
                 size_t out_pstride, LevelStat* __restrict__ lstat, int stat_stride,
                 PlaneStat* __restrict__ pstat, float fg_half_thr) {
-    __shared__ float s_in[AN_INH][AN_INW + 1];
-    __shared__ float s_a[AN_TOY][AN_INW + 1];
-    __shared__ float s_d[AN_TOY][AN_INW + 1];
-    __shared__ float s_red[2][AN_THREADS / 32];
-    __shared__ double s_dred[2][AN_THREADS / 32];
-    __shared__ unsigned s_cred[2][AN_THREADS / 32];
+    __shared__ float s_red[2][AN_WARPS];
+    __shared__ double s_dred[2][AN_WARPS];
+    __shared__ unsigned s_cred[2][AN_WARPS];
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int z = blockIdx.z;
-    const int ox0 = blockIdx.x * AN_TOX;
+    const int ox0 = (blockIdx.x * AN_WARPS + wid) * AN_OXW;
     const int oy0 = blockIdx.y * AN_TOY;
     const IN_T* src = in + (size_t)z * in_pstride;
 
-    double fg_s = 0.0, bg_s = 0.0;
-    unsigned fg_c = 0, bg_c = 0;
+    const int p = ox0 - 2 + lane;  // column pair
+    const int gx0 = 2 * p, gx1 = 2 * p + 1;
+    const int cx0 = reflect_idx(gx0, Ws), cx1 = reflect_idx(gx1, Ws);
+    const bool own0 = (lane >= 2) && (gx0 < Ws);  // pixel ownership for the plane statistics
+    const bool own1 = (lane >= 2) && (gx1 < Ws);
+    // interior pairs are contiguous and aligned: one 32/64-bit load
+    const bool vec_ok = (gx0 >= 0) && (gx1 < Ws) && ((in_pitch & 1) == 0) && ((in_pstride & 1) == 0);
 
-    for (int idx = tid; idx < AN_INH * AN_INW; idx += AN_THREADS) {
-        const int r = idx / AN_INW;
-        const int c = idx - r * AN_INW;
-        const int gy0 = 2 * oy0 - 4 + r;
-        const int gx0 = 2 * ox0 - 4 + c;
-        const int gy = reflect_idx(gy0, Hs);
-        const int gx = reflect_idx(gx0, Ws);
-        float v = (float)src[(size_t)gy * in_pitch + gx];
-        if (FIRST) {
-            // plane statistics: every pixel exactly once (tile interior, un-reflected)
-            if (r >= 4 && r < 4 + 2 * AN_TOY && c >= 4 && c < 4 + 2 * AN_TOX && gy0 < Hs &&
-                gx0 < Ws) {
-                const float hv = __half2float(__float2half_rn(v));
-                if (hv >= fg_half_thr) {
-                    fg_s += (double)v;
-                    fg_c++;
-                } else {
-                    bg_s += (double)v;
-                    bg_c++;
-                }
-            }
-            v = logf(__fadd_rn(1.0f, v));  // np.log(1.0 + x) in float32
-        }
-        s_in[r][c] = v;
-    }
-    __syncthreads();
-
-    // axis -2 (Y)
-    for (int idx = tid; idx < AN_TOY * AN_INW; idx += AN_THREADS) {
-        const int oy = idx / AN_INW;
-        const int c = idx - oy * AN_INW;
-        float a = 0.f, d = 0.f;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const float v = s_in[2 * oy + 5 - j][c];
-            a = fmaf(dec_lo(j), v, a);
-            d = fmaf(dec_hi(j), v, d);
-        }
-        s_a[oy][c] = a;
-        s_d[oy][c] = d;
-    }
-    __syncthreads();
-
-    // axis -1 (X), low-pass only
+    float fg_s = 0.f, all_s = 0.f;  // per-thread partial sums (<= 64 pixels: exact for integers)
+    unsigned fg_c = 0, all_c = 0;
     float qmin = __int_as_float(0x7f800000), qmax = 0.f;
-    float* dA = cA + (size_t)z * out_pstride;
-    float* dH = cH + (size_t)z * out_pstride;
-    for (int idx = tid; idx < AN_TOY * AN_TOX; idx += AN_THREADS) {
-        const int oy = idx / AN_TOX;
-        const int ox = idx - oy * AN_TOX;
-        float a = 0.f, h = 0.f;
+
+    if (ox0 < Wo) {  // warp-uniform
+        float w0[6], w1[6];
+        auto load_row = [&](int r, float& v0, float& v1) {
+            const int gy0 = 2 * oy0 - 4 + r;
+            const IN_T* row = src + (size_t)reflect_idx(gy0, Hs) * in_pitch;
+            if (vec_ok) {
+                load_pair(row + gx0, v0, v1);
+            } else {
+                v0 = (float)row[cx0];
+                v1 = (float)row[cx1];
+            }
+            if (FIRST) {
+                if (STATS) {
+                    if (r >= 4 && gy0 < Hs) {  // rows owned by this tile: [2 oy0, 2 oy0 + 2 AN_TOY)
+                        if (own0) {
+                            const bool fg = __half2float(__float2half_rn(v0)) >= fg_half_thr;
+                            all_s += v0;
+                            all_c++;
+                            if (fg) {
+                                fg_s += v0;
+                                fg_c++;
+                            }
+                        }
+                        if (own1) {
+                            const bool fg = __half2float(__float2half_rn(v1)) >= fg_half_thr;
+                            all_s += v1;
+                            all_c++;
+                            if (fg) {
+                                fg_s += v1;
+                                fg_c++;
+                            }
+                        }
+                    }
+                }
+                v0 = DSTR_LOGF(__fadd_rn(1.0f, v0));  // np.log(1.0 + x) in float32
+                v1 = DSTR_LOGF(__fadd_rn(1.0f, v1));
+            }
+        };
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            a = fmaf(dec_lo(j), s_a[oy][2 * ox + 5 - j], a);
-            h = fmaf(dec_lo(j), s_d[oy][2 * ox + 5 - j], h);
-        }
-        const int goy = oy0 + oy, gox = ox0 + ox;
-        if (goy < Ho && gox < Wo) {
-            dA[(size_t)goy * out_pitch + gox] = a;
-            dH[(size_t)goy * out_pitch + gox] = h;
-            const float q = __fmul_rn(h, h);
-            qmin = fminf(qmin, q);
-            qmax = fmaxf(qmax, q);
+        for (int r = 0; r < 4; ++r) load_row(r, w0[r], w1[r]);
+
+        float* dA = cA + (size_t)z * out_pstride;
+        float* dH = cH + (size_t)z * out_pstride;
+        const int gox = ox0 + lane - 2;
+        const bool col_ok = (lane >= 2) && (gox < Wo);
+#pragma unroll
+        for (int oy = 0; oy < AN_TOY; ++oy) {
+            // rows 2oy+4, 2oy+5 enter the window; row r lives in slot r % 6
+            load_row(2 * oy + 4, w0[(2 * oy + 4) % 6], w1[(2 * oy + 4) % 6]);
+            load_row(2 * oy + 5, w0[(2 * oy + 5) % 6], w1[(2 * oy + 5) % 6]);
+            // axis -2: tap j multiplies input row 2oy + 5 - j
+            float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float v0 = w0[(2 * oy + 5 - j) % 6], v1 = w1[(2 * oy + 5 - j) % 6];
+                a0 = fmaf(dec_lo(j), v0, a0);
+                a1 = fmaf(dec_lo(j), v1, a1);
+                d0 = fmaf(dec_hi(j), v0, d0);
+                d1 = fmaf(dec_hi(j), v1, d1);
+            }
+            // axis -1 (low-pass): taps 0,1 on this pair, 2,3 on lane-1, 4,5 on lane-2
+            const float a0m1 = __shfl_up_sync(0xffffffffu, a0, 1), a1m1 = __shfl_up_sync(0xffffffffu, a1, 1);
+            const float a0m2 = __shfl_up_sync(0xffffffffu, a0, 2), a1m2 = __shfl_up_sync(0xffffffffu, a1, 2);
+            const float d0m1 = __shfl_up_sync(0xffffffffu, d0, 1), d1m1 = __shfl_up_sync(0xffffffffu, d1, 1);
+            const float d0m2 = __shfl_up_sync(0xffffffffu, d0, 2), d1m2 = __shfl_up_sync(0xffffffffu, d1, 2);
+            float ca = 0.f, ch = 0.f;
+            ca = fmaf(dec_lo(0), a1, ca);
+            ca = fmaf(dec_lo(1), a0, ca);
+            ca = fmaf(dec_lo(2), a1m1, ca);
+            ca = fmaf(dec_lo(3), a0m1, ca);
+            ca = fmaf(dec_lo(4), a1m2, ca);
+            ca = fmaf(dec_lo(5), a0m2, ca);
+            ch = fmaf(dec_lo(0), d1, ch);
+            ch = fmaf(dec_lo(1), d0, ch);
+            ch = fmaf(dec_lo(2), d1m1, ch);
+            ch = fmaf(dec_lo(3), d0m1, ch);
+            ch = fmaf(dec_lo(4), d1m2, ch);
+            ch = fmaf(dec_lo(5), d0m2, ch);
+            const int goy = oy0 + oy;
+            if (col_ok && goy < Ho) {
+                dA[(size_t)goy * out_pitch + gox] = ca;
+                dH[(size_t)goy * out_pitch + gox] = ch;
+                const float q = __fmul_rn(ch, ch);
+                qmin = fminf(qmin, q);
+                qmax = fmaxf(qmax, q);
+            }
         }
     }
 
-    // block reductions -> one atomic per block
-    const int lane = tid & 31, wid = tid >> 5;
+    // block reductions -> one set of atomics per block
     qmin = warp_min(qmin);
     qmax = warp_max(qmax);
     if (lane == 0) {
         s_red[0][wid] = qmin;
         s_red[1][wid] = qmax;
     }
-    if (FIRST) {
-        fg_s = warp_sum(fg_s);
-        bg_s = warp_sum(bg_s);
+    if (FIRST && STATS) {
+        const double fs = warp_sum((double)fg_s), as = warp_sum((double)all_s);
         fg_c = __reduce_add_sync(0xffffffffu, fg_c);
-        bg_c = __reduce_add_sync(0xffffffffu, bg_c);
+        all_c = __reduce_add_sync(0xffffffffu, all_c);
         if (lane == 0) {
-            s_dred[0][wid] = fg_s;
-            s_dred[1][wid] = bg_s;
+            s_dred[0][wid] = fs;
+            s_dred[1][wid] = as;
             s_cred[0][wid] = fg_c;
-            s_cred[1][wid] = bg_c;
+            s_cred[1][wid] = all_c;
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         float mn = s_red[0][0], mx = s_red[1][0];
-        for (int w = 1; w < AN_THREADS / 32; ++w) {
+        for (int w = 1; w < AN_WARPS; ++w) {
             mn = fminf(mn, s_red[0][w]);
             mx = fmaxf(mx, s_red[1][w]);
         }
@@ -241,23 +298,23 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
             atomicMax(&st->qmin_inv, ~__float_as_uint(mn));
             atomicMax(&st->qmax_bits, __float_as_uint(mx));
         }
-        if (FIRST) {
-            double fs = 0.0, bs = 0.0;
-            unsigned long long fc = 0, bc = 0;
-            for (int w = 0; w < AN_THREADS / 32; ++w) {
+        if (FIRST && STATS) {
+            double fs = 0.0, as = 0.0;
+            unsigned long long fc = 0, ac = 0;
+            for (int w = 0; w < AN_WARPS; ++w) {
                 fs += s_dred[0][w];
-                bs += s_dred[1][w];
+                as += s_dred[1][w];
                 fc += s_cred[0][w];
-                bc += s_cred[1][w];
+                ac += s_cred[1][w];
             }
             PlaneStat* ps = pstat + z;
             if (fc) {
                 atomicAdd(&ps->fg_sum, fs);
                 atomicAdd(&ps->fg_cnt, fc);
             }
-            if (bc) {
-                atomicAdd(&ps->bg_sum, bs);
-                atomicAdd(&ps->bg_cnt, bc);
+            if (ac - fc) {
+                atomicAdd(&ps->bg_sum, as - fs);
+                atomicAdd(&ps->bg_cnt, ac - fc);
             }
         }
     }
@@ -710,12 +767,21 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
 // synthesis of the deltas: out = idwt2(dA, (dH, 0, 0)) (axis -1 first with rec_lo for both
 // bands, then axis -2 with rec_lo on the dA branch and rec_hi on the dH branch), trimmed to the
 // parent level's shape (pywt.waverec2).  FINAL fuses the inverse log and the epilogue.
+//
+// Register-tiled: one warp owns 64 output columns x SY_TY output rows.  Lane l owns output
+// columns (2m, 2m+1), m = x0/2 + l, which need coefficient columns m, m+1, m+2 (three coalesced,
+// overlapping loads per band and coefficient row) and marches down with a 3-row window.
 // =============================================================================================
 constexpr int SY_TX = 64;
 constexpr int SY_TY = 32;
-constexpr int SY_CW = SY_TX / 2 + 2;  // 34
-constexpr int SY_CH = SY_TY / 2 + 2;  // 18
-constexpr int SY_THREADS = 256;
+constexpr int SY_WARPS = 8;
+constexpr int SY_THREADS = 32 * SY_WARPS;
+
+#ifdef DSTR_FAST_EXP
+#define DSTR_EXPF(x) __expf(x)
+#else
+#define DSTR_EXPF(x) expf(x)
+#endif
 
 struct EpilogueArgs {
     const float* flat;  // nullable
@@ -730,73 +796,119 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
              size_t pstride_l, float* __restrict__ outA, int Ho, int Wo, int pitch_o,
              size_t pstride_o, const IN_T* __restrict__ img, OUT_T* __restrict__ out,
              size_t img_pstride, EpilogueArgs ep) {
-    __shared__ float s_A[SY_CH][SY_CW + 1];
-    __shared__ float s_H[SY_CH][SY_CW + 1];
-    __shared__ float s_L[SY_CH][SY_TX + 1];
-    __shared__ float s_G[SY_CH][SY_TX + 1];
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int z = blockIdx.z;
-    const int x0 = blockIdx.x * SY_TX, y0 = blockIdx.y * SY_TY;
-    const int cx0 = x0 >> 1, cy0 = y0 >> 1;
+    const int x0 = (blockIdx.x * SY_WARPS + wid) * SY_TX;
+    const int y0 = blockIdx.y * SY_TY;
+    if (x0 >= Wo) return;  // warp-uniform; no block-level synchronisation below
+    const int m = (x0 >> 1) + lane;
+    const int cy0 = y0 >> 1;
     const float* pA = dA ? dA + (size_t)z * pstride_l : nullptr;
     const float* pH = dH ? dH + (size_t)z * pstride_l : nullptr;
+    const bool c0 = m < Wl, c1 = m + 1 < Wl, c2 = m + 2 < Wl;
 
-    for (int idx = tid; idx < SY_CH * SY_CW; idx += SY_THREADS) {
-        const int r = idx / SY_CW, c = idx - r * SY_CW;
-        const int gy = cy0 + r, gx = cx0 + c;
-        const bool ok = (gy < Hl) && (gx < Wl);
-        s_A[r][c] = (ok && pA) ? pA[(size_t)gy * pitch_l + gx] : 0.f;
-        s_H[r][c] = (ok && pH) ? pH[(size_t)gy * pitch_l + gx] : 0.f;
-    }
-    __syncthreads();
-    // axis -1
-    for (int idx = tid; idx < SY_CH * SY_TX; idx += SY_THREADS) {
-        const int r = idx / SY_TX, x = idx - r * SY_TX;
-        const int mx = x >> 1, px = x & 1;
-        float l = 0.f, g = 0.f;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float f = px ? rec_lo(2 * j + 1) : rec_lo(2 * j);
-            l = fmaf(f, s_A[r][mx + 2 - j], l);
-            g = fmaf(f, s_H[r][mx + 2 - j], g);
-        }
-        s_L[r][x] = l;
-        s_G[r][x] = g;
-    }
-    __syncthreads();
-    // axis -2 (+ epilogue)
-    for (int idx = tid; idx < SY_TY * SY_TX; idx += SY_THREADS) {
-        const int y = idx / SY_TX, x = idx - y * SY_TX;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= Ho || gx >= Wo) continue;
-        const int my = y >> 1, py = y & 1;
-        float v = 0.f;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float fl = py ? rec_lo(2 * j + 1) : rec_lo(2 * j);
-            const float fh = py ? rec_hi(2 * j + 1) : rec_hi(2 * j);
-            v = fmaf(fl, s_L[my + 2 - j][x], v);
-            v = fmaf(fh, s_G[my + 2 - j][x], v);
-        }
-        if (!FINAL) {
-            outA[(size_t)z * pstride_o + (size_t)gy * pitch_o + gx] = v;
-        } else {
-            // exp(log(1+x) + delta) + 1 == (1+x) * exp(delta) + 1   (filtering.py:175,222)
-            const size_t pix = (size_t)gy * Wo + gx;
-            const float xin = (float)img[(size_t)z * img_pstride + pix];
-            float r = __fmul_rn(__fadd_rn(1.0f, xin), expf(v));
-            r = ep.expm1 ? (r - 1.0f) : (r + 1.0f);
-            if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
-                const float dk = ep.dark[pix];
-                r = (r <= dk) ? 0.f : (r - dk);
-                r = r / ep.flat[pix];
+    // axis -1 for one coefficient row: (L0, L1) from dA, (G0, G1) from dH, columns 2m, 2m+1
+    auto xpass = [&](int r, float& L0, float& L1, float& G0, float& G1) {
+        const int gy = cy0 + r;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        if (gy < Hl) {
+            const size_t o = (size_t)gy * pitch_l + m;
+            if (pA) {
+                if (c0) a0 = pA[o];
+                if (c1) a1 = pA[o + 1];
+                if (c2) a2 = pA[o + 2];
             }
-            if (sizeof(OUT_T) == 2) {
-                r = fminf(fmaxf(r, 0.f), 65535.f);  // np.clip
-                out[(size_t)z * img_pstride + pix] = (OUT_T)(unsigned short)r;  // truncation
+            if (pH) {
+                if (c0) h0 = pH[o];
+                if (c1) h1 = pH[o + 1];
+                if (c2) h2 = pH[o + 2];
+            }
+        }
+        // x = 2m + px: sum_j rec_lo[2j + px] * c[m + 2 - j]
+        L0 = fmaf(rec_lo(0), a2, fmaf(rec_lo(2), a1, rec_lo(4) * a0));
+        L1 = fmaf(rec_lo(1), a2, fmaf(rec_lo(3), a1, rec_lo(5) * a0));
+        G0 = fmaf(rec_lo(0), h2, fmaf(rec_lo(2), h1, rec_lo(4) * h0));
+        G1 = fmaf(rec_lo(1), h2, fmaf(rec_lo(3), h1, rec_lo(5) * h0));
+    };
+
+    float L0[3], L1[3], G0[3], G1[3];
+    xpass(0, L0[0], L1[0], G0[0], G1[0]);
+    xpass(1, L0[1], L1[1], G0[1], G1[1]);
+    const int gx = 2 * m;
+#pragma unroll
+    for (int my = 0; my < SY_TY / 2; ++my) {
+        // coefficient row my+2 enters the window; row r lives in slot r % 3
+        xpass(my + 2, L0[(my + 2) % 3], L1[(my + 2) % 3], G0[(my + 2) % 3], G1[(my + 2) % 3]);
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            const int gy = y0 + 2 * my + py;
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float fl = py ? rec_lo(2 * j + 1) : rec_lo(2 * j);
+                const float fh = py ? rec_hi(2 * j + 1) : rec_hi(2 * j);
+                const int sl = (my + 2 - j) % 3;
+                v0 = fmaf(fl, L0[sl], v0);
+                v0 = fmaf(fh, G0[sl], v0);
+                v1 = fmaf(fl, L1[sl], v1);
+                v1 = fmaf(fh, G1[sl], v1);
+            }
+            if (gy >= Ho) continue;
+            if (!FINAL) {
+                float* o = outA + (size_t)z * pstride_o + (size_t)gy * pitch_o + gx;
+                if (gx < Wo) o[0] = v0;
+                if (gx + 1 < Wo) o[1] = v1;
             } else {
-                if (ep.shadow) r = truncf(fminf(fmaxf(r, 0.f), 65535.f));
-                out[(size_t)z * img_pstride + pix] = (OUT_T)r;
+                const size_t pix = (size_t)gy * Wo + gx;
+                const size_t gpix = (size_t)z * img_pstride + pix;
+                const bool pair = (gx + 1 < Wo) && ((gpix & 1) == 0);
+                float xin0 = 0.f, xin1 = 0.f;
+                if (pair) {
+                    load_pair(img + gpix, xin0, xin1);
+                } else {
+                    if (gx < Wo) xin0 = (float)img[gpix];
+                    if (gx + 1 < Wo) xin1 = (float)img[gpix + 1];
+                }
+                // exp(log(1+x) + delta) + 1 == (1+x) * exp(delta) + 1   (filtering.py:175,222)
+                float r0 = __fmul_rn(__fadd_rn(1.0f, xin0), DSTR_EXPF(v0));
+                float r1 = __fmul_rn(__fadd_rn(1.0f, xin1), DSTR_EXPF(v1));
+                const float one = ep.expm1 ? -1.0f : 1.0f;
+                r0 += one;
+                r1 += one;
+                if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
+                    float dk0 = 0.f, dk1 = 0.f, fl0 = 1.f, fl1 = 1.f;
+                    if (pair && ((pix & 1) == 0)) {
+                        load_pair(ep.dark + pix, dk0, dk1);
+                        load_pair(ep.flat + pix, fl0, fl1);
+                    } else {
+                        if (gx < Wo) {
+                            dk0 = ep.dark[pix];
+                            fl0 = ep.flat[pix];
+                        }
+                        if (gx + 1 < Wo) {
+                            dk1 = ep.dark[pix + 1];
+                            fl1 = ep.flat[pix + 1];
+                        }
+                    }
+                    r0 = (r0 <= dk0) ? 0.f : (r0 - dk0);
+                    r1 = (r1 <= dk1) ? 0.f : (r1 - dk1);
+                    r0 = r0 / fl0;
+                    r1 = r1 / fl1;
+                }
+                if (sizeof(OUT_T) == 2 || ep.shadow) {
+                    r0 = fminf(fmaxf(r0, 0.f), 65535.f);  // np.clip; the u16 conversion truncates
+                    r1 = fminf(fmaxf(r1, 0.f), 65535.f);
+                    if (sizeof(OUT_T) != 2) {
+                        r0 = truncf(r0);
+                        r1 = truncf(r1);
+                    }
+                }
+                if (pair) {
+                    store_pair(out + gpix, r0, r1);
+                } else {
+                    if (gx < Wo) out[gpix] = (OUT_T)r0;
+                    if (gx + 1 < Wo) out[gpix + 1] = (OUT_T)r1;
+                }
             }
         }
     }

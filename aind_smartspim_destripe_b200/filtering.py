@@ -218,18 +218,15 @@ def _resolve_shadow(shadow_correction: dict, input_tile_path, shape):
     return flatfield, darkfield, dark_c
 
 
-_shadow_cache = {}
-
-
 def _engine_with_shadow(eng, shadow_correction, input_tile_path, shape):
+    """Upload flat/dark once per (engine, flat array, dark array); the cache lives on the engine."""
     flat, dark_full, dark_c = _resolve_shadow(shadow_correction, input_tile_path, shape)
-    key = (id(eng), id(flat), id(dark_full))
-    cached = _shadow_cache.get(id(eng))
-    if cached is None or cached[0] != key:
+    cached = getattr(eng, "_shadow_key", None)
+    if cached is None or cached[0] is not flat or cached[1] is not dark_full:
         f32 = np.ascontiguousarray(flat, dtype=np.float32)
         d32 = np.ascontiguousarray(dark_c, dtype=np.float32)
         eng.set_flat_dark(f32, d32)
-        _shadow_cache[id(eng)] = (key, flat, dark_full, f32, d32)  # keep the ids alive
+        eng._shadow_key = (flat, dark_full)  # holding the arrays keeps the identity test valid
 
 
 def filter_planes(
