@@ -555,7 +555,8 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
                 fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
                 const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
                                                      (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
-                                                     (size_t)FR_ROWS * fa.n_pad8 + (size_t)FR_ROWS * fa.Jpad_max) +
+                                                     (size_t)FR_ROWS * fa.n_pad8 + (size_t)FR_ROWS * fa.Jpad_max +
+                                                     (size_t)FR_ROWS * FR_ROWS * fa.Jpad_max) +
                                     (size_t)FR_ROWS * fa.n_pad8;
                 if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
                 const int epl = (g.W + 31) / 32;
@@ -595,7 +596,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
     {
         ScopedTimer t(ctx, 6);
         EpilogueArgs ep;
-        ep.flat = ctx->d_flat;
+        ep.inv_flat = ctx->d_flat;  // stored as the correctly rounded reciprocal
         ep.dark = ctx->d_dark;
         ep.shadow = (flags & DSTR_FLAG_SHADOW) ? 1 : 0;
         ep.expm1 = (flags & DSTR_FLAG_EXPM1) ? 1 : 0;
@@ -786,7 +787,11 @@ int dstr_set_flat_dark(dstr_ctx* ctx, const float* flat, const float* dark) {
     const size_t bytes = sizeof(float) * (size_t)ctx->H * ctx->W;
     if (!ctx->d_flat) CK(ctx, cudaMalloc(&ctx->d_flat, bytes));
     if (!ctx->d_dark) CK(ctx, cudaMalloc(&ctx->d_dark, bytes));
-    CK(ctx, cudaMemcpyAsync(ctx->d_flat, flat, bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+    // the epilogue multiplies by 1/flat (division stays off the device's XU pipe); the
+    // reciprocal is rounded once from double, so x * (1/flat) is within 1 ulp of x / flat
+    std::vector<float> inv((size_t)ctx->H * ctx->W);
+    for (size_t i = 0; i < inv.size(); ++i) inv[i] = (float)(1.0 / (double)flat[i]);
+    CK(ctx, cudaMemcpyAsync(ctx->d_flat, inv.data(), bytes, cudaMemcpyHostToDevice, ctx->s_comp));
     CK(ctx, cudaMemcpyAsync(ctx->d_dark, dark, bytes, cudaMemcpyHostToDevice, ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     ctx->have_flat_dark = true;

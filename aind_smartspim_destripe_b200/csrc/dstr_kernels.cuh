@@ -111,23 +111,63 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- conversions that stay off the quarter-rate XU pipe (no I2F / F2I) --------------------------
+// u16 -> f32: (0x4B000000 | u) is the float 2^23 + u; subtracting 2^23 is exact.
+// f32 in [0, 65535] -> u16 with truncation: (r + 2^23) rounded toward zero has floor(r) in its
+// low mantissa bits.
+__device__ __forceinline__ float u16_to_f32(unsigned u) { return __uint_as_float(0x4B000000u | u) - 8388608.0f; }
+__device__ __forceinline__ unsigned f32_to_u16_trunc(float r) {
+    return __float_as_uint(__fadd_rz(r, 8388608.0f)) & 0xffffu;
+}
+__device__ __forceinline__ float to_f32(unsigned short v) { return u16_to_f32(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+
 // aligned two-element loads / stores (caller guarantees alignment)
 __device__ __forceinline__ void load_pair(const unsigned short* p, float& a, float& b) {
     const unsigned u = *reinterpret_cast<const unsigned*>(p);
-    a = (float)(u & 0xffffu);
-    b = (float)(u >> 16);
+    a = u16_to_f32(u & 0xffffu);
+    b = u16_to_f32(u >> 16);
 }
 __device__ __forceinline__ void load_pair(const float* p, float& a, float& b) {
     const float2 f = *reinterpret_cast<const float2*>(p);
     a = f.x;
     b = f.y;
 }
+// values already clipped to [0, 65535]
 __device__ __forceinline__ void store_pair(unsigned short* p, float a, float b) {
-    *reinterpret_cast<unsigned*>(p) = (unsigned)(unsigned short)a | ((unsigned)(unsigned short)b << 16);
+    *reinterpret_cast<unsigned*>(p) = f32_to_u16_trunc(a) | (f32_to_u16_trunc(b) << 16);
 }
 __device__ __forceinline__ void store_pair(float* p, float a, float b) {
     *reinterpret_cast<float2*>(p) = make_float2(a, b);
 }
+__device__ __forceinline__ void store_one(unsigned short* p, float a) { *p = (unsigned short)f32_to_u16_trunc(a); }
+__device__ __forceinline__ void store_one(float* p, float a) { *p = a; }
+
+template <typename T>
+struct PairOf;
+template <>
+struct PairOf<unsigned short> {
+    typedef unsigned type;
+    __device__ static __forceinline__ unsigned short lo(unsigned w) { return (unsigned short)(w & 0xffffu); }
+    __device__ static __forceinline__ unsigned short hi(unsigned w) { return (unsigned short)(w >> 16); }
+};
+template <>
+struct PairOf<float> {
+    typedef float2 type;
+    __device__ static __forceinline__ float lo(float2 w) { return w.x; }
+    __device__ static __forceinline__ float hi(float2 w) { return w.y; }
+};
+
+// log / exp: the MUFU-based intrinsics are as accurate as the library versions on this path's
+// domain (log argument >= 1: absolute error ~1e-7 + final rounding; |delta| small for exp);
+// -DDSTR_ACCURATE_MATH switches to logf / expf.
+#ifdef DSTR_ACCURATE_MATH
+#define DSTR_LOGF(x) logf(x)
+#define DSTR_EXPF(x) expf(x)
+#else
+#define DSTR_LOGF(x) __logf(x)
+#define DSTR_EXPF(x) __expf(x)
+#endif
 
 // =============================================================================================
 // analysis: one 2-D db3 level, symmetric mode, axis -2 first then axis -1 (pywt.dwt2), keeping
@@ -138,18 +178,12 @@ __device__ __forceinline__ void store_pair(float* p, float a, float b) {
 // the rows with a 6-row sliding window (axis -2 pass: 24 FMA per output row); the axis -1 pass
 // takes the two neighbouring column pairs from lanes l-1 and l-2 by shuffle (8 SHFL + 12 FMA),
 // so lanes 2..31 emit outputs ox0 .. ox0+29.  Halo cost: 4 extra input rows per 2*AN_TOY and
-// 2 of 32 lanes.
+// 2 of 32 lanes.  The row loop is unrolled by 3 (the period of the 6-row window).
 // =============================================================================================
-constexpr int AN_TOY = 16;
+constexpr int AN_TOY = 24;
 constexpr int AN_OXW = 30;  // output columns per warp
 constexpr int AN_WARPS = 8;
 constexpr int AN_THREADS = 32 * AN_WARPS;
-
-#ifdef DSTR_FAST_LOG
-#define DSTR_LOGF(x) __logf(x)
-#else
-#define DSTR_LOGF(x) logf(x)
-#endif
 
 template <typename IN_T, bool FIRST, bool STATS>
 __global__ void __launch_bounds__(AN_THREADS)
@@ -174,96 +208,108 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
     const bool own1 = (lane >= 2) && (gx1 < Ws);
     // interior pairs are contiguous and aligned: one 32/64-bit load
     const bool vec_ok = (gx0 >= 0) && (gx1 < Ws) && ((in_pitch & 1) == 0) && ((in_pstride & 1) == 0);
+    // tiles whose 2*AN_TOY+4 input rows all exist need no row reflection
+    const bool rows_interior = (2 * oy0 - 4 >= 0) && (2 * oy0 + 2 * AN_TOY + 1 < Hs);
 
-    float fg_s = 0.f, all_s = 0.f;  // per-thread partial sums (<= 64 pixels: exact for integers)
+    float fg_s = 0.f, all_s = 0.f;  // per-thread partial sums (<= 96 pixels: exact for integers)
     unsigned fg_c = 0, all_c = 0;
     float qmin = __int_as_float(0x7f800000), qmax = 0.f;
 
     if (ox0 < Wo) {  // warp-uniform
         float w0[6], w1[6];
-        auto load_row = [&](int r, float& v0, float& v1) {
+        // fetch: issue the global loads of input row r (raw values); finish: statistics + log.
+        // The loads of output row oy+1 are issued before the arithmetic of output row oy so that
+        // their latency is covered by the in-order instruction stream of the same warp.
+        auto fetch = [&](int r, IN_T& e0, IN_T& e1) {
             const int gy0 = 2 * oy0 - 4 + r;
-            const IN_T* row = src + (size_t)reflect_idx(gy0, Hs) * in_pitch;
+            const int gy = rows_interior ? gy0 : reflect_idx(gy0, Hs);
+            const IN_T* row = src + (size_t)gy * in_pitch;
             if (vec_ok) {
-                load_pair(row + gx0, v0, v1);
+                const auto two = *reinterpret_cast<const typename PairOf<IN_T>::type*>(row + gx0);
+                e0 = PairOf<IN_T>::lo(two);
+                e1 = PairOf<IN_T>::hi(two);
             } else {
-                v0 = (float)row[cx0];
-                v1 = (float)row[cx1];
+                e0 = row[cx0];
+                e1 = row[cx1];
             }
+        };
+        auto finish = [&](int r, IN_T e0, IN_T e1, float& v0, float& v1) {
+            v0 = to_f32(e0);
+            v1 = to_f32(e1);
             if (FIRST) {
                 if (STATS) {
+                    const int gy0 = 2 * oy0 - 4 + r;
                     if (r >= 4 && gy0 < Hs) {  // rows owned by this tile: [2 oy0, 2 oy0 + 2 AN_TOY)
-                        if (own0) {
-                            const bool fg = __half2float(__float2half_rn(v0)) >= fg_half_thr;
-                            all_s += v0;
-                            all_c++;
-                            if (fg) {
-                                fg_s += v0;
-                                fg_c++;
-                            }
-                        }
-                        if (own1) {
-                            const bool fg = __half2float(__float2half_rn(v1)) >= fg_half_thr;
-                            all_s += v1;
-                            all_c++;
-                            if (fg) {
-                                fg_s += v1;
-                                fg_c++;
-                            }
-                        }
+                        const bool f0 = own0 && (__half2float(__float2half_rn(v0)) >= fg_half_thr);
+                        const bool f1 = own1 && (__half2float(__float2half_rn(v1)) >= fg_half_thr);
+                        all_s += own0 ? v0 : 0.f;
+                        all_s += own1 ? v1 : 0.f;
+                        all_c += (own0 ? 1u : 0u) + (own1 ? 1u : 0u);
+                        fg_s += f0 ? v0 : 0.f;
+                        fg_s += f1 ? v1 : 0.f;
+                        fg_c += (f0 ? 1u : 0u) + (f1 ? 1u : 0u);
                     }
                 }
                 v0 = DSTR_LOGF(__fadd_rn(1.0f, v0));  // np.log(1.0 + x) in float32
                 v1 = DSTR_LOGF(__fadd_rn(1.0f, v1));
             }
         };
+        IN_T e[6][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) load_row(r, w0[r], w1[r]);
+        for (int r = 0; r < 6; ++r) fetch(r, e[r][0], e[r][1]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) finish(r, e[r][0], e[r][1], w0[r], w1[r]);
+        IN_T n40 = e[4][0], n41 = e[4][1], n50 = e[5][0], n51 = e[5][1];  // rows 4, 5 in flight
 
         float* dA = cA + (size_t)z * out_pstride;
         float* dH = cH + (size_t)z * out_pstride;
         const int gox = ox0 + lane - 2;
         const bool col_ok = (lane >= 2) && (gox < Wo);
+        for (int oy3 = 0; oy3 < AN_TOY; oy3 += 3) {
 #pragma unroll
-        for (int oy = 0; oy < AN_TOY; ++oy) {
-            // rows 2oy+4, 2oy+5 enter the window; row r lives in slot r % 6
-            load_row(2 * oy + 4, w0[(2 * oy + 4) % 6], w1[(2 * oy + 4) % 6]);
-            load_row(2 * oy + 5, w0[(2 * oy + 5) % 6], w1[(2 * oy + 5) % 6]);
-            // axis -2: tap j multiplies input row 2oy + 5 - j
-            float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+            for (int k = 0; k < 3; ++k) {
+                const int oy = oy3 + k;  // window slot of input row r is r % 6 == (2k + ..) % 6
+                const IN_T c40 = n40, c41 = n41, c50 = n50, c51 = n51;
+                if (oy + 1 < AN_TOY) {  // prefetch the two rows of the next output row
+                    fetch(2 * oy + 6, n40, n41);
+                    fetch(2 * oy + 7, n50, n51);
+                }
+                finish(2 * oy + 4, c40, c41, w0[(2 * k + 4) % 6], w1[(2 * k + 4) % 6]);
+                finish(2 * oy + 5, c50, c51, w0[(2 * k + 5) % 6], w1[(2 * k + 5) % 6]);
+                // axis -2: tap j multiplies input row 2oy + 5 - j
+                float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const float v0 = w0[(2 * oy + 5 - j) % 6], v1 = w1[(2 * oy + 5 - j) % 6];
-                a0 = fmaf(dec_lo(j), v0, a0);
-                a1 = fmaf(dec_lo(j), v1, a1);
-                d0 = fmaf(dec_hi(j), v0, d0);
-                d1 = fmaf(dec_hi(j), v1, d1);
-            }
-            // axis -1 (low-pass): taps 0,1 on this pair, 2,3 on lane-1, 4,5 on lane-2
-            const float a0m1 = __shfl_up_sync(0xffffffffu, a0, 1), a1m1 = __shfl_up_sync(0xffffffffu, a1, 1);
-            const float a0m2 = __shfl_up_sync(0xffffffffu, a0, 2), a1m2 = __shfl_up_sync(0xffffffffu, a1, 2);
-            const float d0m1 = __shfl_up_sync(0xffffffffu, d0, 1), d1m1 = __shfl_up_sync(0xffffffffu, d1, 1);
-            const float d0m2 = __shfl_up_sync(0xffffffffu, d0, 2), d1m2 = __shfl_up_sync(0xffffffffu, d1, 2);
-            float ca = 0.f, ch = 0.f;
-            ca = fmaf(dec_lo(0), a1, ca);
-            ca = fmaf(dec_lo(1), a0, ca);
-            ca = fmaf(dec_lo(2), a1m1, ca);
-            ca = fmaf(dec_lo(3), a0m1, ca);
-            ca = fmaf(dec_lo(4), a1m2, ca);
-            ca = fmaf(dec_lo(5), a0m2, ca);
-            ch = fmaf(dec_lo(0), d1, ch);
-            ch = fmaf(dec_lo(1), d0, ch);
-            ch = fmaf(dec_lo(2), d1m1, ch);
-            ch = fmaf(dec_lo(3), d0m1, ch);
-            ch = fmaf(dec_lo(4), d1m2, ch);
-            ch = fmaf(dec_lo(5), d0m2, ch);
-            const int goy = oy0 + oy;
-            if (col_ok && goy < Ho) {
-                dA[(size_t)goy * out_pitch + gox] = ca;
-                dH[(size_t)goy * out_pitch + gox] = ch;
-                const float q = __fmul_rn(ch, ch);
-                qmin = fminf(qmin, q);
-                qmax = fmaxf(qmax, q);
+                for (int j = 0; j < 6; ++j) {
+                    const float v0 = w0[(2 * k + 5 - j + 6) % 6], v1 = w1[(2 * k + 5 - j + 6) % 6];
+                    a0 = fmaf(dec_lo(j), v0, a0);
+                    a1 = fmaf(dec_lo(j), v1, a1);
+                    d0 = fmaf(dec_hi(j), v0, d0);
+                    d1 = fmaf(dec_hi(j), v1, d1);
+                }
+                // axis -1 (low-pass): taps 0,1 on this pair, 2,3 on lane-1, 4,5 on lane-2
+                const float a0m1 = __shfl_up_sync(0xffffffffu, a0, 1), a1m1 = __shfl_up_sync(0xffffffffu, a1, 1);
+                const float a0m2 = __shfl_up_sync(0xffffffffu, a0, 2), a1m2 = __shfl_up_sync(0xffffffffu, a1, 2);
+                const float d0m1 = __shfl_up_sync(0xffffffffu, d0, 1), d1m1 = __shfl_up_sync(0xffffffffu, d1, 1);
+                const float d0m2 = __shfl_up_sync(0xffffffffu, d0, 2), d1m2 = __shfl_up_sync(0xffffffffu, d1, 2);
+                float ca = dec_lo(0) * a1, ch = dec_lo(0) * d1;
+                ca = fmaf(dec_lo(1), a0, ca);
+                ca = fmaf(dec_lo(2), a1m1, ca);
+                ca = fmaf(dec_lo(3), a0m1, ca);
+                ca = fmaf(dec_lo(4), a1m2, ca);
+                ca = fmaf(dec_lo(5), a0m2, ca);
+                ch = fmaf(dec_lo(1), d0, ch);
+                ch = fmaf(dec_lo(2), d1m1, ch);
+                ch = fmaf(dec_lo(3), d0m1, ch);
+                ch = fmaf(dec_lo(4), d1m2, ch);
+                ch = fmaf(dec_lo(5), d0m2, ch);
+                const int goy = oy0 + oy;
+                if (col_ok && goy < Ho) {
+                    dA[(size_t)goy * out_pitch + gox] = ca;
+                    dH[(size_t)goy * out_pitch + gox] = ch;
+                    const float q = __fmul_rn(ch, ch);
+                    qmin = fminf(qmin, q);
+                    qmax = fmaxf(qmax, q);
+                }
             }
         }
     }
@@ -333,7 +379,7 @@ plane_stats_kernel(const IN_T* __restrict__ in, int H, int W, size_t pstride,
     double fg_s = 0.0, bg_s = 0.0;
     unsigned fg_c = 0, bg_c = 0;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const float v = (float)src[i];
+        const float v = to_f32(src[i]);
         const float hv = __half2float(__float2half_rn(v));
         if (hv >= fg_half_thr) {
             fg_s += (double)v;
@@ -588,9 +634,10 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     float* s_to = s_te + a.ntap_e_max;                                // [ntap_o_max]
     float* s_E = s_to + a.ntap_o_max;                                 // [FR_ROWS][xlen_e_phys]
     float* s_O = s_E + FR_ROWS * a.xlen_e_phys;                       // [FR_ROWS][xlen_o_phys]
-    float* s_x = s_O + FR_ROWS * a.xlen_o_phys;                       // [FR_ROWS][n_pad8]
+    float* s_x = s_O + FR_ROWS * a.xlen_o_phys;                       // [FR_ROWS][n_pad8]; later XE[nhp4][FR_ROWS]
     float* s_c = s_x + FR_ROWS * a.n_pad8;                            // [FR_ROWS][Jpad_max]
-    unsigned char* s_m = reinterpret_cast<unsigned char*>(s_c + FR_ROWS * a.Jpad_max);  // [FR_ROWS][n_pad8]
+    float* s_part = s_c + FR_ROWS * a.Jpad_max;                       // [FR_ROWS warps][FR_ROWS][Jpad_max]
+    unsigned char* s_m = reinterpret_cast<unsigned char*>(s_part + FR_ROWS * FR_ROWS * a.Jpad_max);  // [FR_ROWS][n_pad8]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int z = blockIdx.y;
@@ -600,10 +647,13 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     const NotchTables nt = cfg ? a.nt[1] : a.nt[0];
     const float thr = a.lstat[(size_t)z * a.stat_stride].thr;
     const int nh = a.nh;
+    const int nhp4 = (nh + 4) & ~3;
 
     for (int i = tid; i < nt.ntap_e; i += FR_THREADS) s_te[i] = nt.te[i];
     for (int i = tid; i < nt.ntap_o; i += FR_THREADS) s_to[i] = nt.to[i];
 
+    float* E = s_E + wid * a.xlen_e_phys;
+    float* O = s_O + wid * a.xlen_o_phys;
     if (wid < nrows) {
         float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
         // ---- load, mask, keys ------------------------------------------------------------
@@ -625,29 +675,71 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             }
         }
         // ---- exact median of the zero-filled background (np.median, filtering.py:201) -------
-        const int k1 = (n - 1) >> 1;
-        unsigned res = 0;
-        for (int b = 31; b >= 0; --b) {
-            const unsigned trial = res | (1u << b);
-            int cnt = 0;
+        // Order statistics k1 = (n-1)/2 and k2 = n/2 of the keys.  The masked entries are exact
+        // zeros sitting in the middle of a roughly symmetric distribution, so the median is very
+        // often 0: test that first.  Otherwise bisect the key bits on the side that holds k1 and
+        // stop as soon as the bracket isolates a single key.
+        const unsigned KZ = 0x80000000u;  // f2key(+0.0f)
+        const int k1 = (n - 1) >> 1, k2 = n >> 1;
+        int cneg = 0, cle0 = 0;
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) cnt += (key[i] < trial) ? 1 : 0;
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (cnt <= k1) res = trial;
+        for (int i = 0; i < EPL; ++i) {
+            cneg += (key[i] < KZ) ? 1 : 0;
+            cle0 += (key[i] <= KZ) ? 1 : 0;
         }
-        float med = key2f(res);
-        if ((n & 1) == 0) {
-            int cle = 0;
-            unsigned nxt = 0xffffffffu;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                cle += (key[i] <= res) ? 1 : 0;
-                if (key[i] > res) nxt = min(nxt, key[i]);
+        cneg = __reduce_add_sync(0xffffffffu, cneg);
+        cle0 = __reduce_add_sync(0xffffffffu, cle0);
+        float med;
+        if (cneg <= k1 && k2 < cle0) {
+            med = 0.f;
+        } else {
+            unsigned res;
+            int lo_cnt, hi_cnt;
+            if (k1 < cneg) {  // negative side: keys in [0, 2^31)
+                res = 0u;
+                lo_cnt = 0;
+                hi_cnt = cneg;
+            } else {  // zero / positive side: keys in [2^31, 2^32)
+                res = KZ;
+                lo_cnt = cneg;
+                hi_cnt = n;
             }
-            cle = __reduce_add_sync(0xffffffffu, cle);
-            nxt = __reduce_min_sync(0xffffffffu, nxt);
-            const unsigned k2 = (cle >= k1 + 2) ? res : nxt;
-            med = (key2f(res) + key2f(k2)) * 0.5f;
+            bool unique = (hi_cnt - lo_cnt) == 1;
+            for (int b = 30; b >= 0 && !unique; --b) {
+                const unsigned trial = res | (1u << b);
+                int cnt = 0;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) cnt += (key[i] < trial) ? 1 : 0;
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (cnt <= k1) {
+                    res = trial;
+                    lo_cnt = cnt;
+                } else {
+                    hi_cnt = cnt;
+                }
+                unique = (hi_cnt - lo_cnt) == 1;
+            }
+            // res is now either the key itself (all bits decided) or a lower bound of the single
+            // key left in the bracket: the smallest key >= res is the k1-th order statistic
+            unsigned kk1 = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                if (key[i] >= res) kk1 = min(kk1, key[i]);
+            kk1 = __reduce_min_sync(0xffffffffu, kk1);
+            med = key2f(kk1);
+            if (k2 != k1) {
+                int cle = 0;
+                unsigned nxt = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    cle += (key[i] <= kk1) ? 1 : 0;
+                    if (key[i] > kk1) nxt = min(nxt, key[i]);
+                }
+                cle = __reduce_add_sync(0xffffffffu, cle);
+                nxt = __reduce_min_sync(0xffffffffu, nxt);
+                const unsigned kk2 = (cle >= k1 + 2) ? kk1 : nxt;
+                med = (key2f(kk1) + key2f(kk2)) * 0.5f;
+            }
         }
         __syncwarp();
         // ---- in-paint ---------------------------------------------------------------------
@@ -655,8 +747,6 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             if (ms[e]) xs[e] = med;
         __syncwarp();
         // ---- even / odd parts, circularly extended:  E[a] = x_e[(a - OFFe) mod n] ----------
-        float* E = s_E + wid * a.xlen_e_phys;
-        float* O = s_O + wid * a.xlen_o_phys;
         {
             const int OFF = nt.ue_lo + nt.ntap_e;
             const int xlen_log = a.nhp8 + nt.ntap_e;
@@ -683,43 +773,63 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 if (t >= n) t -= n;
             }
         }
-        __syncwarp();
-        // ---- rank-J correction coefficients  c_j = sum_v T1[v][j] x_e[v] ---------------------
-        if (nt.J > 0) {
+    }
+    __syncthreads();  // every row's E / O is complete; the s_x rows are dead from here on
+
+    // ---- rank-J correction coefficients  c_j = sum_v T1[v][j] x_e[v], all rows at once ----------
+    if (nt.J > 0) {
+        // XE[v][row] (row-interleaved so that one broadcast LDS.128 serves the four rows)
+        float4* XE = reinterpret_cast<float4*>(s_x);
+        {
             const int OFF = nt.ue_lo + nt.ntap_e;
-            const int nhp4 = (nh + 4) & ~3;
+            float* XEf = s_x;
             for (int v = lane; v < nhp4; v += 32) {
                 const int al = v + OFF;
-                xs[v] = (v <= nh) ? E[al + (al >> 3)] : 0.f;
-            }
-            __syncwarp();
-            const float4* x4 = reinterpret_cast<const float4*>(xs);
-            const int Jpad = nt.Jpad;
-            float* cp = s_c + wid * a.Jpad_max;
-            for (int j0 = 0; j0 < Jpad; j0 += 64) {
-                const bool two = (j0 + 32) < Jpad;
-                const float* t1 = nt.T1 + j0 + lane;
-                float acc0 = 0.f, acc1 = 0.f;
-                for (int v4 = 0; v4 < (nhp4 >> 2); ++v4) {
-                    const float4 xv = x4[v4];
-                    const float* tt = t1 + (size_t)(4 * v4) * Jpad;
-                    acc0 = fmaf(xv.x, __ldg(tt), acc0);
-                    acc0 = fmaf(xv.y, __ldg(tt + Jpad), acc0);
-                    acc0 = fmaf(xv.z, __ldg(tt + 2 * Jpad), acc0);
-                    acc0 = fmaf(xv.w, __ldg(tt + 3 * Jpad), acc0);
-                    if (two) {
-                        acc1 = fmaf(xv.x, __ldg(tt + 32), acc1);
-                        acc1 = fmaf(xv.y, __ldg(tt + Jpad + 32), acc1);
-                        acc1 = fmaf(xv.z, __ldg(tt + 2 * Jpad + 32), acc1);
-                        acc1 = fmaf(xv.w, __ldg(tt + 3 * Jpad + 32), acc1);
-                    }
-                }
-                cp[j0 + lane] = acc0;
-                if (two) cp[j0 + 32 + lane] = acc1;
+                XEf[v * FR_ROWS + wid] = (wid < nrows && v <= nh) ? E[al + (al >> 3)] : 0.f;
             }
         }
+        __syncthreads();
+        const int Jpad = nt.Jpad;
+        const int q = (nhp4 + FR_ROWS - 1) / FR_ROWS;  // v range of this warp
+        const int v_begin = wid * q, v_end = min(nhp4, v_begin + q);
+        for (int j0 = 0; j0 < Jpad; j0 += 64) {
+            const bool two = (j0 + 32) < Jpad;
+            float acc[FR_ROWS][2];
+#pragma unroll
+            for (int r = 0; r < FR_ROWS; ++r) acc[r][0] = acc[r][1] = 0.f;
+            const float* tt = nt.T1 + (size_t)v_begin * Jpad + j0 + lane;
+#pragma unroll 4
+            for (int v = v_begin; v < v_end; ++v) {
+                const float4 xe = XE[v];
+                const float t0 = __ldg(tt);
+                const float t1 = two ? __ldg(tt + 32) : 0.f;
+                tt += Jpad;
+                acc[0][0] = fmaf(xe.x, t0, acc[0][0]);
+                acc[1][0] = fmaf(xe.y, t0, acc[1][0]);
+                acc[2][0] = fmaf(xe.z, t0, acc[2][0]);
+                acc[3][0] = fmaf(xe.w, t0, acc[3][0]);
+                acc[0][1] = fmaf(xe.x, t1, acc[0][1]);
+                acc[1][1] = fmaf(xe.y, t1, acc[1][1]);
+                acc[2][1] = fmaf(xe.z, t1, acc[2][1]);
+                acc[3][1] = fmaf(xe.w, t1, acc[3][1]);
+            }
+#pragma unroll
+            for (int r = 0; r < FR_ROWS; ++r) {
+                float* pp = s_part + ((size_t)wid * FR_ROWS + r) * a.Jpad_max + j0 + lane;
+                pp[0] = acc[r][0];
+                if (two) pp[32] = acc[r][1];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < FR_ROWS * Jpad; i += FR_THREADS) {
+            const int r = i / Jpad, j = i - r * Jpad;
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < FR_ROWS; ++w) sum += s_part[((size_t)w * FR_ROWS + r) * a.Jpad_max + j];
+            s_c[r * a.Jpad_max + j] = sum;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- register-tiled FIRs + rank-J correction over (row, 8-output segment) pairs -----------
     const int nseg = a.nhp8 >> 3;
@@ -735,10 +845,12 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             const float* cp = s_c + r * a.Jpad_max;
             const float4* t2 = reinterpret_cast<const float4*>(nt.T2 + 8 * seg);
             const int stride4 = a.nhp8 >> 2;
+#pragma unroll 4
             for (int j = 0; j < nt.J; ++j) {
                 const float c = cp[j];
-                const float4 u0 = __ldg(t2 + (size_t)j * stride4);
-                const float4 u1 = __ldg(t2 + (size_t)j * stride4 + 1);
+                const float4 u0 = __ldg(t2);
+                const float4 u1 = __ldg(t2 + 1);
+                t2 += stride4;
                 ye[0] = fmaf(c, u0.x, ye[0]);
                 ye[1] = fmaf(c, u0.y, ye[1]);
                 ye[2] = fmaf(c, u0.z, ye[2]);
@@ -770,24 +882,19 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
 //
 // Register-tiled: one warp owns 64 output columns x SY_TY output rows.  Lane l owns output
 // columns (2m, 2m+1), m = x0/2 + l, which need coefficient columns m, m+1, m+2 (three coalesced,
-// overlapping loads per band and coefficient row) and marches down with a 3-row window.
+// overlapping loads per band and coefficient row) and marches down with a 3-row window (row
+// loop unrolled by 3).
 // =============================================================================================
 constexpr int SY_TX = 64;
-constexpr int SY_TY = 32;
+constexpr int SY_TY = 48;
 constexpr int SY_WARPS = 8;
 constexpr int SY_THREADS = 32 * SY_WARPS;
 
-#ifdef DSTR_FAST_EXP
-#define DSTR_EXPF(x) __expf(x)
-#else
-#define DSTR_EXPF(x) expf(x)
-#endif
-
 struct EpilogueArgs {
-    const float* flat;  // nullable
-    const float* dark;  // nullable
-    int shadow;         // apply dark/flat
-    int expm1;          // exp(y) - 1 instead of exp(y) + 1
+    const float* inv_flat;  // nullable; 1 / flatfield
+    const float* dark;      // nullable
+    int shadow;             // apply dark/flat
+    int expm1;              // exp(y) - 1 instead of exp(y) + 1
 };
 
 template <bool FINAL, typename IN_T, typename OUT_T>
@@ -803,111 +910,144 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
     if (x0 >= Wo) return;  // warp-uniform; no block-level synchronisation below
     const int m = (x0 >> 1) + lane;
     const int cy0 = y0 >> 1;
-    const float* pA = dA ? dA + (size_t)z * pstride_l : nullptr;
-    const float* pH = dH ? dH + (size_t)z * pstride_l : nullptr;
+    const float* pA = dA ? dA + (size_t)z * pstride_l + m : nullptr;
+    const float* pH = dH ? dH + (size_t)z * pstride_l + m : nullptr;
     const bool c0 = m < Wl, c1 = m + 1 < Wl, c2 = m + 2 < Wl;
 
-    // axis -1 for one coefficient row: (L0, L1) from dA, (G0, G1) from dH, columns 2m, 2m+1
-    auto xpass = [&](int r, float& L0, float& L1, float& G0, float& G1) {
+    // fetch: issue the six coefficient loads of coefficient row r; xpass: axis -1 synthesis of
+    // that row -> (L0, L1) from dA, (G0, G1) from dH for output columns 2m, 2m+1.  Row r+1 is
+    // fetched before row r is consumed (software pipelining of the in-order warp).
+    auto fetch = [&](int r, float (&c)[6]) {
         const int gy = cy0 + r;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c[i] = 0.f;
         if (gy < Hl) {
-            const size_t o = (size_t)gy * pitch_l + m;
+            const size_t o = (size_t)gy * pitch_l;
             if (pA) {
-                if (c0) a0 = pA[o];
-                if (c1) a1 = pA[o + 1];
-                if (c2) a2 = pA[o + 2];
+                if (c0) c[0] = pA[o];
+                if (c1) c[1] = pA[o + 1];
+                if (c2) c[2] = pA[o + 2];
             }
             if (pH) {
-                if (c0) h0 = pH[o];
-                if (c1) h1 = pH[o + 1];
-                if (c2) h2 = pH[o + 2];
+                if (c0) c[3] = pH[o];
+                if (c1) c[4] = pH[o + 1];
+                if (c2) c[5] = pH[o + 2];
             }
         }
+    };
+    auto xpass = [&](const float (&c)[6], float& L0, float& L1, float& G0, float& G1) {
         // x = 2m + px: sum_j rec_lo[2j + px] * c[m + 2 - j]
-        L0 = fmaf(rec_lo(0), a2, fmaf(rec_lo(2), a1, rec_lo(4) * a0));
-        L1 = fmaf(rec_lo(1), a2, fmaf(rec_lo(3), a1, rec_lo(5) * a0));
-        G0 = fmaf(rec_lo(0), h2, fmaf(rec_lo(2), h1, rec_lo(4) * h0));
-        G1 = fmaf(rec_lo(1), h2, fmaf(rec_lo(3), h1, rec_lo(5) * h0));
+        L0 = fmaf(rec_lo(0), c[2], fmaf(rec_lo(2), c[1], rec_lo(4) * c[0]));
+        L1 = fmaf(rec_lo(1), c[2], fmaf(rec_lo(3), c[1], rec_lo(5) * c[0]));
+        G0 = fmaf(rec_lo(0), c[5], fmaf(rec_lo(2), c[4], rec_lo(4) * c[3]));
+        G1 = fmaf(rec_lo(1), c[5], fmaf(rec_lo(3), c[4], rec_lo(5) * c[3]));
     };
 
     float L0[3], L1[3], G0[3], G1[3];
-    xpass(0, L0[0], L1[0], G0[0], G1[0]);
-    xpass(1, L0[1], L1[1], G0[1], G1[1]);
+    float cn[6];  // coefficient row in flight
+    {
+        float ca[6], cb[6];
+        fetch(0, ca);
+        fetch(1, cb);
+        fetch(2, cn);
+        xpass(ca, L0[0], L1[0], G0[0], G1[0]);
+        xpass(cb, L0[1], L1[1], G0[1], G1[1]);
+    }
     const int gx = 2 * m;
+    const bool v0ok = gx < Wo, v1ok = gx + 1 < Wo;
+    const float one = ep.expm1 ? -1.0f : 1.0f;
+    for (int my3 = 0; my3 < SY_TY / 2; my3 += 3) {
 #pragma unroll
-    for (int my = 0; my < SY_TY / 2; ++my) {
-        // coefficient row my+2 enters the window; row r lives in slot r % 3
-        xpass(my + 2, L0[(my + 2) % 3], L1[(my + 2) % 3], G0[(my + 2) % 3], G1[(my + 2) % 3]);
+        for (int k = 0; k < 3; ++k) {
+            const int my = my3 + k;
+            float cc[6];
 #pragma unroll
-        for (int py = 0; py < 2; ++py) {
-            const int gy = y0 + 2 * my + py;
-            float v0 = 0.f, v1 = 0.f;
+            for (int i = 0; i < 6; ++i) cc[i] = cn[i];
+            if (my + 1 < SY_TY / 2) fetch(my + 3, cn);
+            // image pixels of the two output rows of this step (FINAL): issue the loads now
+            float xin[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            if (FINAL) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float fl = py ? rec_lo(2 * j + 1) : rec_lo(2 * j);
-                const float fh = py ? rec_hi(2 * j + 1) : rec_hi(2 * j);
-                const int sl = (my + 2 - j) % 3;
-                v0 = fmaf(fl, L0[sl], v0);
-                v0 = fmaf(fh, G0[sl], v0);
-                v1 = fmaf(fl, L1[sl], v1);
-                v1 = fmaf(fh, G1[sl], v1);
+                for (int py = 0; py < 2; ++py) {
+                    const int gy = y0 + 2 * my + py;
+                    if (gy < Ho) {
+                        const size_t gpix = (size_t)z * img_pstride + (size_t)gy * Wo + gx;
+                        if (v1ok && ((gpix & 1) == 0)) {
+                            load_pair(img + gpix, xin[py][0], xin[py][1]);
+                        } else {
+                            if (v0ok) xin[py][0] = to_f32(img[gpix]);
+                            if (v1ok) xin[py][1] = to_f32(img[gpix + 1]);
+                        }
+                    }
+                }
             }
-            if (gy >= Ho) continue;
-            if (!FINAL) {
-                float* o = outA + (size_t)z * pstride_o + (size_t)gy * pitch_o + gx;
-                if (gx < Wo) o[0] = v0;
-                if (gx + 1 < Wo) o[1] = v1;
-            } else {
-                const size_t pix = (size_t)gy * Wo + gx;
-                const size_t gpix = (size_t)z * img_pstride + pix;
-                const bool pair = (gx + 1 < Wo) && ((gpix & 1) == 0);
-                float xin0 = 0.f, xin1 = 0.f;
-                if (pair) {
-                    load_pair(img + gpix, xin0, xin1);
-                } else {
-                    if (gx < Wo) xin0 = (float)img[gpix];
-                    if (gx + 1 < Wo) xin1 = (float)img[gpix + 1];
+            // coefficient row my+2 enters the window; row r lives in slot r % 3
+            xpass(cc, L0[(k + 2) % 3], L1[(k + 2) % 3], G0[(k + 2) % 3], G1[(k + 2) % 3]);
+#pragma unroll
+            for (int py = 0; py < 2; ++py) {
+                const int gy = y0 + 2 * my + py;
+                float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float fl = py ? rec_lo(2 * j + 1) : rec_lo(2 * j);
+                    const float fh = py ? rec_hi(2 * j + 1) : rec_hi(2 * j);
+                    const int sl = (k + 2 - j + 3) % 3;
+                    v0 = fmaf(fl, L0[sl], v0);
+                    v0 = fmaf(fh, G0[sl], v0);
+                    v1 = fmaf(fl, L1[sl], v1);
+                    v1 = fmaf(fh, G1[sl], v1);
                 }
-                // exp(log(1+x) + delta) + 1 == (1+x) * exp(delta) + 1   (filtering.py:175,222)
-                float r0 = __fmul_rn(__fadd_rn(1.0f, xin0), DSTR_EXPF(v0));
-                float r1 = __fmul_rn(__fadd_rn(1.0f, xin1), DSTR_EXPF(v1));
-                const float one = ep.expm1 ? -1.0f : 1.0f;
-                r0 += one;
-                r1 += one;
-                if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
-                    float dk0 = 0.f, dk1 = 0.f, fl0 = 1.f, fl1 = 1.f;
-                    if (pair && ((pix & 1) == 0)) {
-                        load_pair(ep.dark + pix, dk0, dk1);
-                        load_pair(ep.flat + pix, fl0, fl1);
+                if (gy >= Ho) continue;
+                if (!FINAL) {
+                    float* o = outA + (size_t)z * pstride_o + (size_t)gy * pitch_o + gx;
+                    if (v1ok && ((pitch_o & 1) == 0) && ((pstride_o & 1) == 0)) {
+                        store_pair(o, v0, v1);
                     } else {
-                        if (gx < Wo) {
-                            dk0 = ep.dark[pix];
-                            fl0 = ep.flat[pix];
-                        }
-                        if (gx + 1 < Wo) {
-                            dk1 = ep.dark[pix + 1];
-                            fl1 = ep.flat[pix + 1];
-                        }
+                        if (v0ok) o[0] = v0;
+                        if (v1ok) o[1] = v1;
                     }
-                    r0 = (r0 <= dk0) ? 0.f : (r0 - dk0);
-                    r1 = (r1 <= dk1) ? 0.f : (r1 - dk1);
-                    r0 = r0 / fl0;
-                    r1 = r1 / fl1;
-                }
-                if (sizeof(OUT_T) == 2 || ep.shadow) {
-                    r0 = fminf(fmaxf(r0, 0.f), 65535.f);  // np.clip; the u16 conversion truncates
-                    r1 = fminf(fmaxf(r1, 0.f), 65535.f);
-                    if (sizeof(OUT_T) != 2) {
-                        r0 = truncf(r0);
-                        r1 = truncf(r1);
-                    }
-                }
-                if (pair) {
-                    store_pair(out + gpix, r0, r1);
                 } else {
-                    if (gx < Wo) out[gpix] = (OUT_T)r0;
-                    if (gx + 1 < Wo) out[gpix + 1] = (OUT_T)r1;
+                    const size_t pix = (size_t)gy * Wo + gx;
+                    const size_t gpix = (size_t)z * img_pstride + pix;
+                    const bool pair = v1ok && ((gpix & 1) == 0);
+                    const float xin0 = xin[py][0], xin1 = xin[py][1];
+                    // exp(log(1+x) + delta) + 1 == (1+x) * exp(delta) + 1   (filtering.py:175,222)
+                    float r0 = fmaf(__fadd_rn(1.0f, xin0), DSTR_EXPF(v0), one);
+                    float r1 = fmaf(__fadd_rn(1.0f, xin1), DSTR_EXPF(v1), one);
+                    if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
+                        float dk0 = 0.f, dk1 = 0.f, if0 = 1.f, if1 = 1.f;
+                        if (pair && ((pix & 1) == 0)) {
+                            load_pair(ep.dark + pix, dk0, dk1);
+                            load_pair(ep.inv_flat + pix, if0, if1);
+                        } else {
+                            if (v0ok) {
+                                dk0 = ep.dark[pix];
+                                if0 = ep.inv_flat[pix];
+                            }
+                            if (v1ok) {
+                                dk1 = ep.dark[pix + 1];
+                                if1 = ep.inv_flat[pix + 1];
+                            }
+                        }
+                        r0 = (r0 <= dk0) ? 0.f : (r0 - dk0);
+                        r1 = (r1 <= dk1) ? 0.f : (r1 - dk1);
+                        r0 *= if0;
+                        r1 *= if1;
+                    }
+                    if (sizeof(OUT_T) == 2 || ep.shadow) {
+                        r0 = fminf(fmaxf(r0, 0.f), 65535.f);  // np.clip; the u16 conversion truncates
+                        r1 = fminf(fmaxf(r1, 0.f), 65535.f);
+                        if (sizeof(OUT_T) != 2) {
+                            r0 = truncf(r0);
+                            r1 = truncf(r1);
+                        }
+                    }
+                    if (pair) {
+                        store_pair(out + gpix, r0, r1);
+                    } else {
+                        if (v0ok) store_one(out + gpix, r0);
+                        if (v1ok) store_one(out + gpix + 1, r1);
+                    }
                 }
             }
         }
