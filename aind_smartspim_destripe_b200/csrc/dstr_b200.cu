@@ -477,27 +477,39 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
         ScopedTimer t(ctx, l == 1 ? 0 : 1);
         const LevelGeom& gs = ctx->geom[l - 1];
         const LevelGeom& go = ctx->geom[l];
-        const int cols_per_block = AN_OXW * AN_WARPS;
-        dim3 grid((go.W + cols_per_block - 1) / cols_per_block, (go.H + AN_TOY - 1) / AN_TOY, z);
+        const int cols_per_block = AN_OXW * AN_WX, rows_per_block = AN_TOY * AN_WY;
+        dim3 grid((go.W + cols_per_block - 1) / cols_per_block, (go.H + rows_per_block - 1) / rows_per_block, z);
         LevelStat* ls = ctx->d_lstat + (size_t)(l - 1) * level_stride;
         const bool stats = dp.mode == 1;
-#define LAUNCH_AN1(IN_T, ST)                                                                          \
-    analysis_kernel<IN_T, true, ST><<<grid, AN_THREADS, 0, st>>>(                                      \
+#define LAUNCH_AN1(IN_T, ST, VEC)                                                                     \
+    analysis_kernel<IN_T, true, ST, VEC><<<grid, AN_THREADS, 0, st>>>(                                 \
         (const IN_T*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W, go.pitch,     \
         go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr)
+#define LAUNCH_AN1V(IN_T, ST)        \
+    do {                             \
+        if (vec) LAUNCH_AN1(IN_T, ST, true); \
+        else LAUNCH_AN1(IN_T, ST, false);    \
+    } while (0)
+        // aligned two-element loads need an even width, pitch and plane stride
+        const bool vec = (gs.W % 2 == 0) && (gs.W >= 8) && (gs.H >= 8) && (gs.pitch % 2 == 0) && (gs.pstride % 2 == 0);
         if (l == 1) {
             if (in_dtype == DSTR_U16) {
-                if (stats) LAUNCH_AN1(uint16_t, true);
-                else LAUNCH_AN1(uint16_t, false);
+                if (stats) LAUNCH_AN1V(uint16_t, true);
+                else LAUNCH_AN1V(uint16_t, false);
             } else {
-                if (stats) LAUNCH_AN1(float, true);
-                else LAUNCH_AN1(float, false);
+                if (stats) LAUNCH_AN1V(float, true);
+                else LAUNCH_AN1V(float, false);
             }
+        } else if (vec) {
+            analysis_kernel<float, false, false, true><<<grid, AN_THREADS, 0, st>>>(
+                ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H,
+                go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
         } else {
-            analysis_kernel<float, false, false><<<grid, AN_THREADS, 0, st>>>(
+            analysis_kernel<float, false, false, false><<<grid, AN_THREADS, 0, st>>>(
                 ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H,
                 go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
         }
+#undef LAUNCH_AN1V
 #undef LAUNCH_AN1
         ctx->launches++;
         CK(ctx, cudaGetLastError());
@@ -582,7 +594,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
                 const LevelGeom& go = ctx->geom[l - 1];
                 dim3 grid((go.W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (go.H + SY_TY - 1) / SY_TY, z);
                 const float* dA = (l == L) ? nullptr : ctx->d_A[l];
-                synth_kernel<false, float, float><<<grid, SY_THREADS, 0, st>>>(
+                synth_kernel<false, float, float, false><<<grid, SY_THREADS, 0, st>>>(
                     dA, ctx->d_H[l], g.H, g.W, g.pitch, g.pstride, ctx->d_A[l - 1], go.H, go.W,
                     go.pitch, go.pstride, nullptr, nullptr, 0, ep0);
                 ctx->launches++;
@@ -605,14 +617,21 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
         const float* dH = (L >= 1) ? ctx->d_H[1] : nullptr;
         dim3 grid((W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (H + SY_TY - 1) / SY_TY, z);
         const size_t ps = (size_t)H * W;
-#define LAUNCH_FINAL(IN_T, OUT_T)                                                                   \
-    synth_kernel<true, IN_T, OUT_T><<<grid, SY_THREADS, 0, st>>>(                                   \
-        dA, dH, g.H, g.W, g.pitch, g.pstride, nullptr, H, W, W, ps, (const IN_T*)d_in, (OUT_T*)d_out, \
+#define LAUNCH_FINAL_V(IN_T, OUT_T, VEC)                                                               \
+    synth_kernel<true, IN_T, OUT_T, VEC><<<grid, SY_THREADS, 0, st>>>(                                 \
+        dA, dH, g.H, g.W, g.pitch, g.pstride, nullptr, H, W, W, ps, (const IN_T*)d_in, (OUT_T*)d_out,  \
         ps, ep)
+#define LAUNCH_FINAL(IN_T, OUT_T)                 \
+    do {                                          \
+        if (vecf) LAUNCH_FINAL_V(IN_T, OUT_T, true);  \
+        else LAUNCH_FINAL_V(IN_T, OUT_T, false);      \
+    } while (0)
+        const bool vecf = (W % 2 == 0) && (W >= 2) && (ps % 2 == 0);
         if (in_dtype == DSTR_U16 && out_dtype == DSTR_U16) LAUNCH_FINAL(uint16_t, uint16_t);
         else if (in_dtype == DSTR_U16 && out_dtype == DSTR_F32) LAUNCH_FINAL(uint16_t, float);
         else if (in_dtype == DSTR_F32 && out_dtype == DSTR_U16) LAUNCH_FINAL(float, uint16_t);
         else LAUNCH_FINAL(float, float);
+#undef LAUNCH_FINAL_V
 #undef LAUNCH_FINAL
         ctx->launches++;
         CK(ctx, cudaGetLastError());

@@ -77,13 +77,9 @@ struct DispatchParams {
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
-    // half-sample symmetric extension, repeated for short signals
-    if (i < 0 || i >= n) {
-        const int p = 2 * n;
-        i %= p;
-        if (i < 0) i += p;
-        if (i >= n) i = p - 1 - i;
-    }
+    // half-sample symmetric extension (x[-1-k] = x[k], x[n+k] = x[n-1-k]), repeated for short
+    // signals; division-free: one reflection suffices unless the signal is shorter than the halo
+    while (i < 0 || i >= n) i = (i < 0) ? (-1 - i) : (2 * n - 1 - i);
     return i;
 }
 
@@ -182,10 +178,52 @@ struct PairOf<float> {
 // =============================================================================================
 constexpr int AN_TOY = 24;
 constexpr int AN_OXW = 30;  // output columns per warp
-constexpr int AN_WARPS = 8;
+constexpr int AN_WX = 2;    // warps of a block along x ...
+constexpr int AN_WY = 4;    // ... and along y
+constexpr int AN_WARPS = AN_WX * AN_WY;
 constexpr int AN_THREADS = 32 * AN_WARPS;
 
-template <typename IN_T, bool FIRST, bool STATS>
+// single reflection + clamp: exact for every index a valid output needs when n >= 8 (rows or
+// columns past that are only touched by outputs that are discarded)
+__device__ __forceinline__ int reflect_fast(int i, int n) {
+    i = (i < 0) ? (-1 - i) : i;
+    i = (i >= n) ? (2 * n - 1 - i) : i;
+    return max(0, min(i, n - 1));
+}
+
+// raw (unconverted) two-column loads: the conversion is deferred to the point of use so that the
+// in-order warp does not stall on the load right after issuing it
+template <typename IN_T, bool VEC>
+struct RawPair;
+template <typename IN_T>
+struct RawPair<IN_T, true> {
+    typename PairOf<IN_T>::type w;
+    __device__ __forceinline__ void load(const IN_T* row, int c0, int /*c1*/) {
+        w = *reinterpret_cast<const typename PairOf<IN_T>::type*>(row + c0);
+    }
+    __device__ __forceinline__ void get(bool swp, float& v0, float& v1) const {
+        const float a = to_f32(PairOf<IN_T>::lo(w)), b = to_f32(PairOf<IN_T>::hi(w));
+        v0 = swp ? b : a;
+        v1 = swp ? a : b;
+    }
+};
+template <typename IN_T>
+struct RawPair<IN_T, false> {
+    IN_T a, b;
+    __device__ __forceinline__ void load(const IN_T* row, int c0, int c1) {
+        a = row[c0];
+        b = row[c1];
+    }
+    __device__ __forceinline__ void get(bool, float& v0, float& v1) const {
+        v0 = to_f32(a);
+        v1 = to_f32(b);
+    }
+};
+
+// VEC: Hs, Ws >= 8, Ws even, even pitch / plane stride: every (reflected) column pair is an aligned
+// two-element word, possibly swapped, and one reflection per index suffices; otherwise two scalar
+// loads per row with the general (repeated) reflection.
+template <typename IN_T, bool FIRST, bool STATS, bool VEC>
 __global__ void __launch_bounds__(AN_THREADS)
 analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_t in_pstride,
                 float* __restrict__ cA, float* __restrict__ cH, int Ho, int Wo, int out_pitch,
@@ -197,45 +235,51 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int z = blockIdx.z;
-    const int ox0 = (blockIdx.x * AN_WARPS + wid) * AN_OXW;
-    const int oy0 = blockIdx.y * AN_TOY;
+    const int ox0 = (blockIdx.x * AN_WX + (wid % AN_WX)) * AN_OXW;
+    const int oy0 = (blockIdx.y * AN_WY + (wid / AN_WX)) * AN_TOY;
     const IN_T* src = in + (size_t)z * in_pstride;
 
-    const int p = ox0 - 2 + lane;  // column pair
+    const int p = ox0 - 2 + lane;  // column pair (2p, 2p+1)
     const int gx0 = 2 * p, gx1 = 2 * p + 1;
-    const int cx0 = reflect_idx(gx0, Ws), cx1 = reflect_idx(gx1, Ws);
+    int c0, c1;
+    bool swp = false;
+    if (VEC) {
+        // reflected pair: (2p, 2p+1) -> (2q+1, 2q) with q = -1-p (left) or Ws-1-p (right, Ws even)
+        int q = p;
+        if (p < 0) {
+            q = -1 - p;
+            swp = true;
+        } else if (gx1 >= Ws) {
+            q = Ws - 1 - p;
+            swp = true;
+        }
+        q = max(0, min(q, Ws / 2 - 1));  // lanes of strips past the right edge: any valid address
+        c0 = 2 * q;
+        c1 = c0 + 1;
+    } else {
+        c0 = reflect_idx(gx0, Ws);
+        c1 = reflect_idx(gx1, Ws);
+    }
     const bool own0 = (lane >= 2) && (gx0 < Ws);  // pixel ownership for the plane statistics
     const bool own1 = (lane >= 2) && (gx1 < Ws);
-    // interior pairs are contiguous and aligned: one 32/64-bit load
-    const bool vec_ok = (gx0 >= 0) && (gx1 < Ws) && ((in_pitch & 1) == 0) && ((in_pstride & 1) == 0);
-    // tiles whose 2*AN_TOY+4 input rows all exist need no row reflection
-    const bool rows_interior = (2 * oy0 - 4 >= 0) && (2 * oy0 + 2 * AN_TOY + 1 < Hs);
 
     float fg_s = 0.f, all_s = 0.f;  // per-thread partial sums (<= 96 pixels: exact for integers)
     unsigned fg_c = 0, all_c = 0;
     float qmin = __int_as_float(0x7f800000), qmax = 0.f;
 
-    if (ox0 < Wo) {  // warp-uniform
+    if (ox0 < Wo && oy0 < Ho) {  // warp-uniform
+        typedef RawPair<IN_T, VEC> Raw;
         float w0[6], w1[6];
-        // fetch: issue the global loads of input row r (raw values); finish: statistics + log.
+        const IN_T* lane_base = src + (VEC ? c0 : 0);
+        // fetch: issue the global loads of input row r (raw); finish: convert, statistics, log.
         // The loads of output row oy+1 are issued before the arithmetic of output row oy so that
         // their latency is covered by the in-order instruction stream of the same warp.
-        auto fetch = [&](int r, IN_T& e0, IN_T& e1) {
-            const int gy0 = 2 * oy0 - 4 + r;
-            const int gy = rows_interior ? gy0 : reflect_idx(gy0, Hs);
-            const IN_T* row = src + (size_t)gy * in_pitch;
-            if (vec_ok) {
-                const auto two = *reinterpret_cast<const typename PairOf<IN_T>::type*>(row + gx0);
-                e0 = PairOf<IN_T>::lo(two);
-                e1 = PairOf<IN_T>::hi(two);
-            } else {
-                e0 = row[cx0];
-                e1 = row[cx1];
-            }
+        auto fetch = [&](int r, Raw& e) {
+            const int gy = VEC ? reflect_fast(2 * oy0 - 4 + r, Hs) : reflect_idx(2 * oy0 - 4 + r, Hs);
+            e.load(lane_base + (unsigned)(gy * in_pitch), VEC ? 0 : c0, c1);
         };
-        auto finish = [&](int r, IN_T e0, IN_T e1, float& v0, float& v1) {
-            v0 = to_f32(e0);
-            v1 = to_f32(e1);
+        auto finish = [&](int r, const Raw& e, float& v0, float& v1) {
+            e.get(swp, v0, v1);
             if (FIRST) {
                 if (STATS) {
                     const int gy0 = 2 * oy0 - 4 + r;
@@ -254,28 +298,28 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
                 v1 = DSTR_LOGF(__fadd_rn(1.0f, v1));
             }
         };
-        IN_T e[6][2];
+        Raw e[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) fetch(r, e[r][0], e[r][1]);
+        for (int r = 0; r < 6; ++r) fetch(r, e[r]);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) finish(r, e[r][0], e[r][1], w0[r], w1[r]);
-        IN_T n40 = e[4][0], n41 = e[4][1], n50 = e[5][0], n51 = e[5][1];  // rows 4, 5 in flight
+        for (int r = 0; r < 4; ++r) finish(r, e[r], w0[r], w1[r]);
+        Raw n4 = e[4], n5 = e[5];  // rows 4, 5 in flight
 
-        float* dA = cA + (size_t)z * out_pstride;
-        float* dH = cH + (size_t)z * out_pstride;
         const int gox = ox0 + lane - 2;
         const bool col_ok = (lane >= 2) && (gox < Wo);
+        float* oA = cA + (size_t)z * out_pstride + (size_t)oy0 * out_pitch + gox;
+        float* oH = cH + (size_t)z * out_pstride + (size_t)oy0 * out_pitch + gox;
         for (int oy3 = 0; oy3 < AN_TOY; oy3 += 3) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int oy = oy3 + k;  // window slot of input row r is r % 6 == (2k + ..) % 6
-                const IN_T c40 = n40, c41 = n41, c50 = n50, c51 = n51;
+                const Raw c4 = n4, c5 = n5;
                 if (oy + 1 < AN_TOY) {  // prefetch the two rows of the next output row
-                    fetch(2 * oy + 6, n40, n41);
-                    fetch(2 * oy + 7, n50, n51);
+                    fetch(2 * oy + 6, n4);
+                    fetch(2 * oy + 7, n5);
                 }
-                finish(2 * oy + 4, c40, c41, w0[(2 * k + 4) % 6], w1[(2 * k + 4) % 6]);
-                finish(2 * oy + 5, c50, c51, w0[(2 * k + 5) % 6], w1[(2 * k + 5) % 6]);
+                finish(2 * oy + 4, c4, w0[(2 * k + 4) % 6], w1[(2 * k + 4) % 6]);
+                finish(2 * oy + 5, c5, w0[(2 * k + 5) % 6], w1[(2 * k + 5) % 6]);
                 // axis -2: tap j multiplies input row 2oy + 5 - j
                 float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -302,14 +346,15 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
                 ch = fmaf(dec_lo(3), d0m1, ch);
                 ch = fmaf(dec_lo(4), d1m2, ch);
                 ch = fmaf(dec_lo(5), d0m2, ch);
-                const int goy = oy0 + oy;
-                if (col_ok && goy < Ho) {
-                    dA[(size_t)goy * out_pitch + gox] = ca;
-                    dH[(size_t)goy * out_pitch + gox] = ch;
+                if (col_ok && oy0 + oy < Ho) {
+                    *oA = ca;
+                    *oH = ch;
                     const float q = __fmul_rn(ch, ch);
                     qmin = fminf(qmin, q);
                     qmax = fmaxf(qmax, q);
                 }
+                oA += out_pitch;
+                oH += out_pitch;
             }
         }
     }
@@ -897,7 +942,9 @@ struct EpilogueArgs {
     int expm1;              // exp(y) - 1 instead of exp(y) + 1
 };
 
-template <bool FINAL, typename IN_T, typename OUT_T>
+// VEC (FINAL only): Wo and the plane stride are even, so the two pixels of a lane are one aligned
+// word of the image, of the output and of the dark / flat fields.
+template <bool FINAL, typename IN_T, typename OUT_T, bool VEC>
 __global__ void __launch_bounds__(SY_THREADS)
 synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl, int Wl, int pitch_l,
              size_t pstride_l, float* __restrict__ outA, int Ho, int Wo, int pitch_o,
@@ -907,40 +954,47 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
     const int z = blockIdx.z;
     const int x0 = (blockIdx.x * SY_WARPS + wid) * SY_TX;
     const int y0 = blockIdx.y * SY_TY;
-    if (x0 >= Wo) return;  // warp-uniform; no block-level synchronisation below
+    if (x0 >= Wo) return;  // no block-level synchronisation below
     const int m = (x0 >> 1) + lane;
     const int cy0 = y0 >> 1;
-    const float* pA = dA ? dA + (size_t)z * pstride_l + m : nullptr;
-    const float* pH = dH ? dH + (size_t)z * pstride_l + m : nullptr;
+    // clamped coefficient columns: out-of-range columns only feed discarded outputs or are
+    // multiplied by the zero that replaces them below
     const bool c0 = m < Wl, c1 = m + 1 < Wl, c2 = m + 2 < Wl;
+    const int mc = min(m, Wl - 1);
+    const float* pA = dA ? dA + (size_t)z * pstride_l + mc : nullptr;
+    const float* pH = dH ? dH + (size_t)z * pstride_l + mc : nullptr;
+    const int o1 = c1 ? 1 : 0, o2 = c2 ? 2 : 0;
 
-    // fetch: issue the six coefficient loads of coefficient row r; xpass: axis -1 synthesis of
-    // that row -> (L0, L1) from dA, (G0, G1) from dH for output columns 2m, 2m+1.  Row r+1 is
-    // fetched before row r is consumed (software pipelining of the in-order warp).
+    // fetch: issue the six coefficient loads of coefficient row r (row r+1 is fetched before row r
+    // is consumed: software pipelining of the in-order warp); xpass: axis -1 synthesis of that row
+    // -> (L0, L1) from dA, (G0, G1) from dH for output columns 2m, 2m+1.
     auto fetch = [&](int r, float (&c)[6]) {
-        const int gy = cy0 + r;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) c[i] = 0.f;
-        if (gy < Hl) {
-            const size_t o = (size_t)gy * pitch_l;
-            if (pA) {
-                if (c0) c[0] = pA[o];
-                if (c1) c[1] = pA[o + 1];
-                if (c2) c[2] = pA[o + 2];
-            }
-            if (pH) {
-                if (c0) c[3] = pH[o];
-                if (c1) c[4] = pH[o + 1];
-                if (c2) c[5] = pH[o + 2];
-            }
+        const int gy = min(cy0 + r, Hl - 1);
+        const unsigned o = (unsigned)(gy * pitch_l);
+        if (pA) {
+            c[0] = pA[o];
+            c[1] = pA[o + o1];
+            c[2] = pA[o + o2];
+        } else {
+            c[0] = c[1] = c[2] = 0.f;
+        }
+        if (pH) {
+            c[3] = pH[o];
+            c[4] = pH[o + o1];
+            c[5] = pH[o + o2];
+        } else {
+            c[3] = c[4] = c[5] = 0.f;
         }
     };
-    auto xpass = [&](const float (&c)[6], float& L0, float& L1, float& G0, float& G1) {
+    auto xpass = [&](int r, const float (&c)[6], float& L0, float& L1, float& G0, float& G1) {
+        const bool rok = (cy0 + r) < Hl;
+        const float a0 = (rok && c0) ? c[0] : 0.f, a1 = (rok && c1) ? c[1] : 0.f, a2 = (rok && c2) ? c[2] : 0.f;
+        const float h0 = (rok && c0) ? c[3] : 0.f, h1 = (rok && c1) ? c[4] : 0.f, h2 = (rok && c2) ? c[5] : 0.f;
         // x = 2m + px: sum_j rec_lo[2j + px] * c[m + 2 - j]
-        L0 = fmaf(rec_lo(0), c[2], fmaf(rec_lo(2), c[1], rec_lo(4) * c[0]));
-        L1 = fmaf(rec_lo(1), c[2], fmaf(rec_lo(3), c[1], rec_lo(5) * c[0]));
-        G0 = fmaf(rec_lo(0), c[5], fmaf(rec_lo(2), c[4], rec_lo(4) * c[3]));
-        G1 = fmaf(rec_lo(1), c[5], fmaf(rec_lo(3), c[4], rec_lo(5) * c[3]));
+        L0 = fmaf(rec_lo(0), a2, fmaf(rec_lo(2), a1, rec_lo(4) * a0));
+        L1 = fmaf(rec_lo(1), a2, fmaf(rec_lo(3), a1, rec_lo(5) * a0));
+        G0 = fmaf(rec_lo(0), h2, fmaf(rec_lo(2), h1, rec_lo(4) * h0));
+        G1 = fmaf(rec_lo(1), h2, fmaf(rec_lo(3), h1, rec_lo(5) * h0));
     };
 
     float L0[3], L1[3], G0[3], G1[3];
@@ -950,12 +1004,16 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
         fetch(0, ca);
         fetch(1, cb);
         fetch(2, cn);
-        xpass(ca, L0[0], L1[0], G0[0], G1[0]);
-        xpass(cb, L0[1], L1[1], G0[1], G1[1]);
+        xpass(0, ca, L0[0], L1[0], G0[0], G1[0]);
+        xpass(1, cb, L0[1], L1[1], G0[1], G1[1]);
     }
     const int gx = 2 * m;
     const bool v0ok = gx < Wo, v1ok = gx + 1 < Wo;
     const float one = ep.expm1 ? -1.0f : 1.0f;
+    typedef RawPair<IN_T, VEC> Raw;
+    // per-lane image / output cursors (FINAL), advanced by one row at a time
+    const int gxc = min(gx, Wo - (VEC ? 2 : 1));
+    const int gx1c = min(gx + 1, Wo - 1);
     for (int my3 = 0; my3 < SY_TY / 2; my3 += 3) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -964,25 +1022,19 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
 #pragma unroll
             for (int i = 0; i < 6; ++i) cc[i] = cn[i];
             if (my + 1 < SY_TY / 2) fetch(my + 3, cn);
-            // image pixels of the two output rows of this step (FINAL): issue the loads now
-            float xin[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            // raw image pixels of the two output rows of this step (FINAL): issue the loads now,
+            // convert after the synthesis arithmetic
+            Raw px[2];
             if (FINAL) {
 #pragma unroll
                 for (int py = 0; py < 2; ++py) {
-                    const int gy = y0 + 2 * my + py;
-                    if (gy < Ho) {
-                        const size_t gpix = (size_t)z * img_pstride + (size_t)gy * Wo + gx;
-                        if (v1ok && ((gpix & 1) == 0)) {
-                            load_pair(img + gpix, xin[py][0], xin[py][1]);
-                        } else {
-                            if (v0ok) xin[py][0] = to_f32(img[gpix]);
-                            if (v1ok) xin[py][1] = to_f32(img[gpix + 1]);
-                        }
-                    }
+                    const int gy = min(y0 + 2 * my + py, Ho - 1);
+                    const IN_T* rowp = img + (size_t)z * img_pstride + (unsigned)(gy * Wo);
+                    px[py].load(rowp + (VEC ? gxc : 0), VEC ? 0 : gxc, gx1c);
                 }
             }
             // coefficient row my+2 enters the window; row r lives in slot r % 3
-            xpass(cc, L0[(k + 2) % 3], L1[(k + 2) % 3], G0[(k + 2) % 3], G1[(k + 2) % 3]);
+            xpass(my + 2, cc, L0[(k + 2) % 3], L1[(k + 2) % 3], G0[(k + 2) % 3], G1[(k + 2) % 3]);
 #pragma unroll
             for (int py = 0; py < 2; ++py) {
                 const int gy = y0 + 2 * my + py;
@@ -997,33 +1049,27 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
                     v1 = fmaf(fl, L1[sl], v1);
                     v1 = fmaf(fh, G1[sl], v1);
                 }
-                if (gy >= Ho) continue;
+                if (gy >= Ho || !v0ok) continue;
                 if (!FINAL) {
-                    float* o = outA + (size_t)z * pstride_o + (size_t)gy * pitch_o + gx;
-                    if (v1ok && ((pitch_o & 1) == 0) && ((pstride_o & 1) == 0)) {
-                        store_pair(o, v0, v1);
-                    } else {
-                        if (v0ok) o[0] = v0;
-                        if (v1ok) o[1] = v1;
-                    }
+                    // pitch_o is a multiple of 4 and gx is even: the pair store stays inside the row
+                    float* o = outA + (size_t)z * pstride_o + (unsigned)(gy * pitch_o) + gx;
+                    store_pair(o, v0, v1);
                 } else {
-                    const size_t pix = (size_t)gy * Wo + gx;
+                    const unsigned pix = (unsigned)(gy * Wo) + gx;
                     const size_t gpix = (size_t)z * img_pstride + pix;
-                    const bool pair = v1ok && ((gpix & 1) == 0);
-                    const float xin0 = xin[py][0], xin1 = xin[py][1];
+                    float xin0, xin1;
+                    px[py].get(false, xin0, xin1);
                     // exp(log(1+x) + delta) + 1 == (1+x) * exp(delta) + 1   (filtering.py:175,222)
                     float r0 = fmaf(__fadd_rn(1.0f, xin0), DSTR_EXPF(v0), one);
                     float r1 = fmaf(__fadd_rn(1.0f, xin1), DSTR_EXPF(v1), one);
                     if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
-                        float dk0 = 0.f, dk1 = 0.f, if0 = 1.f, if1 = 1.f;
-                        if (pair && ((pix & 1) == 0)) {
+                        float dk0, dk1 = 0.f, if0, if1 = 1.f;
+                        if (VEC) {
                             load_pair(ep.dark + pix, dk0, dk1);
                             load_pair(ep.inv_flat + pix, if0, if1);
                         } else {
-                            if (v0ok) {
-                                dk0 = ep.dark[pix];
-                                if0 = ep.inv_flat[pix];
-                            }
+                            dk0 = ep.dark[pix];
+                            if0 = ep.inv_flat[pix];
                             if (v1ok) {
                                 dk1 = ep.dark[pix + 1];
                                 if1 = ep.inv_flat[pix + 1];
@@ -1042,10 +1088,10 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
                             r1 = truncf(r1);
                         }
                     }
-                    if (pair) {
+                    if (VEC) {
                         store_pair(out + gpix, r0, r1);
                     } else {
-                        if (v0ok) store_one(out + gpix, r0);
+                        store_one(out + gpix, r0);
                         if (v1ok) store_one(out + gpix + 1, r1);
                     }
                 }
