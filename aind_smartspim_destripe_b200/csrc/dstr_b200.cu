@@ -567,9 +567,8 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
                 fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
                 const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
                                                      (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
-                                                     (size_t)FR_ROWS * fa.n_pad8 + (size_t)FR_ROWS * fa.Jpad_max +
-                                                     (size_t)FR_ROWS * FR_ROWS * fa.Jpad_max) +
-                                    (size_t)FR_ROWS * fa.n_pad8;
+                                                     (size_t)FR_ROWS * fa.Jpad_max +
+                                                     (size_t)FR_ROWS * FR_ROWS * fa.Jpad_max);
                 if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
                 const int epl = (g.W + 31) / 32;
                 int rc;

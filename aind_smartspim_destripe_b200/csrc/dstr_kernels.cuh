@@ -58,7 +58,8 @@ struct LevelStat {
     float otsu_raw;      // skimage threshold_otsu(cH^2)
     float thr;           // min(max_threshold, sqrt(otsu_raw))
     int otsu_bin;
-    int pad[3];
+    float thr_q;         // largest float q with sqrt_rn(q) <= thr:  sqrt(c*c) > thr  <=>  c*c > thr_q
+    int pad[2];
     unsigned hist[256];
 };
 
@@ -591,7 +592,20 @@ otsu_kernel(LevelStat* __restrict__ lstat_base, size_t level_stride, int stat_st
         const float sq = __fsqrt_rn(otsu);
         st->otsu_raw = otsu;
         st->otsu_bin = best_i;
-        st->thr = (sq < max_thr) ? sq : max_thr;  // python min(max_threshold, sqrt)
+        const float thr = (sq < max_thr) ? sq : max_thr;  // python min(max_threshold, sqrt)
+        st->thr = thr;
+        // the mask test sqrt_rn(c*c) > thr (filtering.py:187-195) as a test on q = c*c: sqrt_rn is
+        // monotone, so it equals q > T with T the largest float whose rounded root is <= thr
+        float T = __fmul_rn(thr, thr);
+        if (thr >= 0.f && thr < __int_as_float(0x7f800000)) {
+            for (int it = 0; it < 8 && __fsqrt_rn(T) > thr; ++it) T = __uint_as_float(__float_as_uint(T) - 1u);
+            for (int it = 0; it < 8; ++it) {
+                const float Tn = __uint_as_float(__float_as_uint(T) + 1u);
+                if (!(__fsqrt_rn(Tn) <= thr)) break;
+                T = Tn;
+            }
+        }
+        st->thr_q = T;
     }
 }
 
@@ -675,14 +689,12 @@ __global__ void __launch_bounds__(FR_THREADS)
 filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.Wl;
-    float* s_te = reinterpret_cast<float*>(smem_raw);                 // [ntap_e_max]
-    float* s_to = s_te + a.ntap_e_max;                                // [ntap_o_max]
-    float* s_E = s_to + a.ntap_o_max;                                 // [FR_ROWS][xlen_e_phys]
-    float* s_O = s_E + FR_ROWS * a.xlen_e_phys;                       // [FR_ROWS][xlen_o_phys]
-    float* s_x = s_O + FR_ROWS * a.xlen_o_phys;                       // [FR_ROWS][n_pad8]; later XE[nhp4][FR_ROWS]
-    float* s_c = s_x + FR_ROWS * a.n_pad8;                            // [FR_ROWS][Jpad_max]
-    float* s_part = s_c + FR_ROWS * a.Jpad_max;                       // [FR_ROWS warps][FR_ROWS][Jpad_max]
-    unsigned char* s_m = reinterpret_cast<unsigned char*>(s_part + FR_ROWS * FR_ROWS * a.Jpad_max);  // [FR_ROWS][n_pad8]
+    float* s_te = reinterpret_cast<float*>(smem_raw);   // [ntap_e_max]
+    float* s_to = s_te + a.ntap_e_max;                  // [ntap_o_max]
+    float* s_E = s_to + a.ntap_o_max;                   // [FR_ROWS][xlen_e_phys]
+    float* s_O = s_E + FR_ROWS * a.xlen_e_phys;         // [FR_ROWS][xlen_o_phys]
+    float* s_c = s_O + FR_ROWS * a.xlen_o_phys;         // [FR_ROWS][Jpad_max]
+    float* s_part = s_c + FR_ROWS * a.Jpad_max;         // [FR_ROWS warps][FR_ROWS][Jpad_max]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int z = blockIdx.y;
@@ -690,9 +702,9 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     const int nrows = min(FR_ROWS, a.Hl - row0);
     const int cfg = plane_uses_cells(pstat[z], dp);
     const NotchTables nt = cfg ? a.nt[1] : a.nt[0];
-    const float thr = a.lstat[(size_t)z * a.stat_stride].thr;
+    // mask rule sqrt(c*c) > thr evaluated as c*c > thr_q (bit-identical, see otsu_kernel)
+    const float thr_q = a.lstat[(size_t)z * a.stat_stride].thr_q;
     const int nh = a.nh;
-    const int nhp4 = (nh + 4) & ~3;
 
     for (int i = tid; i < nt.ntap_e; i += FR_THREADS) s_te[i] = nt.te[i];
     for (int i = tid; i < nt.ntap_o; i += FR_THREADS) s_to[i] = nt.to[i];
@@ -700,23 +712,17 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     float* E = s_E + wid * a.xlen_e_phys;
     float* O = s_O + wid * a.xlen_o_phys;
     if (wid < nrows) {
-        float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
+        const float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
         // ---- load, mask, keys ------------------------------------------------------------
         unsigned key[EPL];
-        float* xs = s_x + wid * a.n_pad8;
-        unsigned char* ms = s_m + wid * a.n_pad8;
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
             const int e = lane + 32 * i;
             key[i] = 0xffffffffu;
             if (e < n) {
                 const float c = grow[e];
-                const float p = __fsqrt_rn(__fmul_rn(c, c));
-                const bool m = p > thr;
-                const float bg = m ? 0.0f : (c + 0.0f);  // canonical +0
-                key[i] = f2key(bg);
-                xs[e] = c;
-                ms[e] = m ? 1 : 0;
+                const bool m = __fmul_rn(c, c) > thr_q;
+                key[i] = f2key(m ? 0.0f : (c + 0.0f));  // zero-filled background, canonical +0
             }
         }
         // ---- exact median of the zero-filled background (np.median, filtering.py:201) -------
@@ -786,57 +792,39 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 med = (key2f(kk1) + key2f(kk2)) * 0.5f;
             }
         }
-        __syncwarp();
-        // ---- in-paint ---------------------------------------------------------------------
-        for (int e = lane; e < n; e += 32)
-            if (ms[e]) xs[e] = med;
-        __syncwarp();
-        // ---- even / odd parts, circularly extended:  E[a] = x_e[(a - OFFe) mod n] ----------
+        // ---- in-painted row x[t] = m ? med : c, split into circular even / odd parts and stored
+        //      circularly extended for the FIRs:  E[tau + OFFe] = x_e[tau mod n], same for O.
+        //      The row is re-read from global memory (L1-resident) instead of being staged.
         {
-            const int OFF = nt.ue_lo + nt.ntap_e;
-            const int xlen_log = a.nhp8 + nt.ntap_e;
-            int t = (lane - OFF) % n;
+            const int OFFe = nt.ue_lo + nt.ntap_e, OFFo = nt.uo_lo + nt.ntap_o;
+            const int len_e = a.nhp8 + nt.ntap_e, len_o = a.nhp8 + nt.ntap_o;
+            const int tau_lo = -max(OFFe, OFFo);
+            const int tau_hi = max(len_e - OFFe, len_o - OFFo);
+            int t = (tau_lo + lane) % n;
             if (t < 0) t += n;
             const int step = 32 % n;
-            for (int al = lane; al < xlen_log; al += 32) {
+            for (int tau = tau_lo + lane; tau < tau_hi; tau += 32) {
                 const int tr = (t == 0) ? 0 : n - t;
-                E[al + (al >> 3)] = 0.5f * (xs[t] + xs[tr]);
-                t += step;
-                if (t >= n) t -= n;
-            }
-        }
-        {
-            const int OFF = nt.uo_lo + nt.ntap_o;
-            const int xlen_log = a.nhp8 + nt.ntap_o;
-            int t = (lane - OFF) % n;
-            if (t < 0) t += n;
-            const int step = 32 % n;
-            for (int al = lane; al < xlen_log; al += 32) {
-                const int tr = (t == 0) ? 0 : n - t;
-                O[al + (al >> 3)] = 0.5f * (xs[t] - xs[tr]);
+                const float c1 = grow[t], c2 = grow[tr];
+                const float x1 = (__fmul_rn(c1, c1) > thr_q) ? med : c1;
+                const float x2 = (__fmul_rn(c2, c2) > thr_q) ? med : c2;
+                const int ae = tau + OFFe, ao = tau + OFFo;
+                if (ae >= 0 && ae < len_e) E[ae + (ae >> 3)] = 0.5f * (x1 + x2);
+                if (ao >= 0 && ao < len_o) O[ao + (ao >> 3)] = 0.5f * (x1 - x2);
                 t += step;
                 if (t >= n) t -= n;
             }
         }
     }
-    __syncthreads();  // every row's E / O is complete; the s_x rows are dead from here on
+    __syncthreads();  // every row's E / O is complete
 
     // ---- rank-J correction coefficients  c_j = sum_v T1[v][j] x_e[v], all rows at once ----------
     if (nt.J > 0) {
-        // XE[v][row] (row-interleaved so that one broadcast LDS.128 serves the four rows)
-        float4* XE = reinterpret_cast<float4*>(s_x);
-        {
-            const int OFF = nt.ue_lo + nt.ntap_e;
-            float* XEf = s_x;
-            for (int v = lane; v < nhp4; v += 32) {
-                const int al = v + OFF;
-                XEf[v * FR_ROWS + wid] = (wid < nrows && v <= nh) ? E[al + (al >> 3)] : 0.f;
-            }
-        }
-        __syncthreads();
+        const int OFFe = nt.ue_lo + nt.ntap_e;
         const int Jpad = nt.Jpad;
-        const int q = (nhp4 + FR_ROWS - 1) / FR_ROWS;  // v range of this warp
-        const int v_begin = wid * q, v_end = min(nhp4, v_begin + q);
+        const int nv = nh + 1;
+        const int q = (nv + FR_ROWS - 1) / FR_ROWS;  // v range of this warp
+        const int v_begin = wid * q, v_end = min(nv, v_begin + q);
         for (int j0 = 0; j0 < Jpad; j0 += 64) {
             const bool two = (j0 + 32) < Jpad;
             float acc[FR_ROWS][2];
@@ -845,18 +833,17 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             const float* tt = nt.T1 + (size_t)v_begin * Jpad + j0 + lane;
 #pragma unroll 4
             for (int v = v_begin; v < v_end; ++v) {
-                const float4 xe = XE[v];
+                const int al = v + OFFe;
+                const int ph = al + (al >> 3);
                 const float t0 = __ldg(tt);
                 const float t1 = two ? __ldg(tt + 32) : 0.f;
                 tt += Jpad;
-                acc[0][0] = fmaf(xe.x, t0, acc[0][0]);
-                acc[1][0] = fmaf(xe.y, t0, acc[1][0]);
-                acc[2][0] = fmaf(xe.z, t0, acc[2][0]);
-                acc[3][0] = fmaf(xe.w, t0, acc[3][0]);
-                acc[0][1] = fmaf(xe.x, t1, acc[0][1]);
-                acc[1][1] = fmaf(xe.y, t1, acc[1][1]);
-                acc[2][1] = fmaf(xe.z, t1, acc[2][1]);
-                acc[3][1] = fmaf(xe.w, t1, acc[3][1]);
+#pragma unroll
+                for (int r = 0; r < FR_ROWS; ++r) {
+                    const float xe = s_E[r * a.xlen_e_phys + ph];  // broadcast; rows >= nrows unused
+                    acc[r][0] = fmaf(xe, t0, acc[r][0]);
+                    acc[r][1] = fmaf(xe, t1, acc[r][1]);
+                }
             }
 #pragma unroll
             for (int r = 0; r < FR_ROWS; ++r) {
@@ -906,15 +893,20 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 ye[7] = fmaf(c, u1.w, ye[7]);
             }
         }
+        // dH[t] = masked ? 0 : -(B x)[t]; the mask is re-derived from the coefficient about to be
+        // overwritten (each element is read and written by this thread only)
         float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + r) * a.pitch;
-        const unsigned char* ms = s_m + r * a.n_pad8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int t = 8 * seg + i;
             if (t <= nh) {
-                orow[t] = ms[t] ? 0.f : -(ye[i] + yo[i]);
+                const float c = orow[t];
+                orow[t] = (__fmul_rn(c, c) > thr_q) ? 0.f : -(ye[i] + yo[i]);
                 const int tm = n - t;
-                if (t != 0 && tm != t) orow[tm] = ms[tm] ? 0.f : -(ye[i] - yo[i]);
+                if (t != 0 && tm != t) {
+                    const float cm = orow[tm];
+                    orow[tm] = (__fmul_rn(cm, cm) > thr_q) ? 0.f : -(ye[i] - yo[i]);
+                }
             }
         }
     }
