@@ -522,7 +522,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
             ScopedTimer t(ctx, 2);
             for (int l = 1; l <= L; ++l) {
                 const LevelGeom& g = ctx->geom[l];
-                const int nblk = std::max(1, std::min(g.H, (g.H * g.W + 8191) / 8192));
+                const int nblk = std::max(1, (g.H * (g.pitch / 4) + 2047) / 2048);  // ~8 quads per thread
                 dim3 grid(nblk, z);
                 hist_kernel<<<grid, 256, 0, st>>>(ctx->d_H[l], g.H, g.W, g.pitch, g.pstride,
                                                   ctx->d_lstat + (size_t)(l - 1) * level_stride,
@@ -740,8 +740,9 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         g.pitch = (g.W + 3) & ~3;
         g.pstride = (size_t)g.H * g.pitch;
         ctx->geom[l] = g;
-        CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * g.pstride * max_planes));
-        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * g.pstride * max_planes));
+        // + 8 floats of slack: the synthesis kernel reads columns m+1, m+2 unconditionally
+        CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * (g.pstride * max_planes + 8)));
+        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 8)));
     }
     if (ctx->Lmax > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lmax * max_planes));
     CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));

@@ -158,12 +158,22 @@ struct PairOf<float> {
 // log / exp: the MUFU-based intrinsics are as accurate as the library versions on this path's
 // domain (log argument >= 1: absolute error ~1e-7 + final rounding; |delta| small for exp);
 // -DDSTR_ACCURATE_MATH switches to logf / expf.
+__device__ __forceinline__ float fast_log(float x) {  // x >= 1 on this path: no denormal scaling
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.6931471805599453f;
+}
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 #ifdef DSTR_ACCURATE_MATH
 #define DSTR_LOGF(x) logf(x)
 #define DSTR_EXPF(x) expf(x)
 #else
-#define DSTR_LOGF(x) __logf(x)
-#define DSTR_EXPF(x) __expf(x)
+#define DSTR_LOGF(x) fast_log(x)
+#define DSTR_EXPF(x) fast_exp(x)
 #endif
 
 // =============================================================================================
@@ -315,10 +325,10 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
             for (int k = 0; k < 3; ++k) {
                 const int oy = oy3 + k;  // window slot of input row r is r % 6 == (2k + ..) % 6
                 const Raw c4 = n4, c5 = n5;
-                if (oy + 1 < AN_TOY) {  // prefetch the two rows of the next output row
-                    fetch(2 * oy + 6, n4);
-                    fetch(2 * oy + 7, n5);
-                }
+                // prefetch the two rows of the next output row (row indices are reflected / clamped,
+                // so the loads past the last output row are harmless and stay unconditional)
+                fetch(2 * oy + 6, n4);
+                fetch(2 * oy + 7, n5);
                 finish(2 * oy + 4, c4, w0[(2 * k + 4) % 6], w1[(2 * k + 4) % 6]);
                 finish(2 * oy + 5, c5, w0[(2 * k + 5) % 6], w1[(2 * k + 5) % 6]);
                 // axis -2: tap j multiplies input row 2oy + 5 - j
@@ -487,6 +497,33 @@ __device__ __forceinline__ float hist_edge(int i, float first, float last, float
     return __double2float_rn(y);
 }
 
+// One bin index with np.histogram semantics: arithmetic guess, then the +-1 fix-ups against the
+// float32 edges decide (the guess only has to land within one bin of the answer, so a reciprocal
+// multiply replaces numpy's division without changing the result).
+__device__ __forceinline__ int hist_bin(float v, float first, float inv_width, const float* s_edges) {
+    const float q = __fmul_rn(v, v);
+    int idx = (int)(__fsub_rn(q, first) * inv_width);
+    idx = max(0, min(idx, 255));
+    if (q < s_edges[idx]) {
+        idx = max(idx - 1, 0);
+    } else if (idx != 255 && q >= s_edges[idx + 1]) {
+        idx++;
+    }
+    return idx;
+}
+
+// Warp-level accumulation tuned for the extremely skewed distribution of cH^2 (most samples in
+// the first bins): the bin of the first active lane is counted for all its peers with one
+// ballot, the remaining lanes use shared-memory atomics.
+__device__ __forceinline__ void hist_add(unsigned* s_hist, int idx, int lane) {
+    const unsigned act = __ballot_sync(0xffffffffu, idx >= 0);
+    if (act == 0) return;
+    const int b0 = __shfl_sync(0xffffffffu, idx, __ffs(act) - 1);
+    const unsigned same = __ballot_sync(0xffffffffu, idx == b0);
+    if (lane == __ffs(act) - 1) atomicAdd(&s_hist[b0], __popc(same));
+    if (idx >= 0 && idx != b0) atomicAdd(&s_hist[idx], 1u);
+}
+
 __global__ void __launch_bounds__(256)
 hist_kernel(const float* __restrict__ cH, int Hl, int Wl, int pitch, size_t pstride,
             LevelStat* __restrict__ lstat, int stat_stride) {
@@ -504,28 +541,28 @@ hist_kernel(const float* __restrict__ cH, int Hl, int Wl, int pitch, size_t pstr
     s_hist[tid] = 0;
     __syncthreads();
 
+    const float inv_width = 256.0f / delta;
     const float* src = cH + (size_t)z * pstride;
     const int lane = tid & 31;
-    const int wl_up = (Wl + 255) & ~255;
-    for (int r = blockIdx.x; r < Hl; r += gridDim.x) {
-        const float* row = src + (size_t)r * pitch;
-        for (int c = tid; c < wl_up; c += 256) {
-            int idx = -1;
-            if (c < Wl) {
-                const float v = row[c];
-                const float q = __fmul_rn(v, v);
-                const float f = __fmul_rn(__fdiv_rn(__fsub_rn(q, first), delta), 256.0f);
-                idx = (int)f;
-                idx = max(0, min(idx, 255));
-                if (q < s_edges[idx]) {
-                    idx = max(idx - 1, 0);
-                } else if (idx != 255 && q >= s_edges[idx + 1]) {
-                    idx++;
-                }
-            }
-            const unsigned peers = __match_any_sync(0xffffffffu, idx);
-            if (idx >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&s_hist[idx], __popc(peers));
+    // the band is walked as float4 quads over the padded rows (pitch % 4 == 0, 16-byte aligned)
+    const int qpr = pitch >> 2;  // quads per row
+    const int nquads = Hl * qpr;
+    const int nq_up = (nquads + 255) & ~255;
+    for (int qi = blockIdx.x * 256 + tid; qi < nq_up; qi += gridDim.x * 256) {
+        int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+        if (qi < nquads) {
+            const int r = qi / qpr;
+            const int c = (qi - r * qpr) << 2;
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * pitch + c);
+            if (c < Wl) i0 = hist_bin(v.x, first, inv_width, s_edges);
+            if (c + 1 < Wl) i1 = hist_bin(v.y, first, inv_width, s_edges);
+            if (c + 2 < Wl) i2 = hist_bin(v.z, first, inv_width, s_edges);
+            if (c + 3 < Wl) i3 = hist_bin(v.w, first, inv_width, s_edges);
         }
+        hist_add(s_hist, i0, lane);
+        hist_add(s_hist, i1, lane);
+        hist_add(s_hist, i2, lane);
+        hist_add(s_hist, i3, lane);
     }
     __syncthreads();
     const unsigned h = s_hist[tid];
@@ -959,21 +996,25 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
 
     // fetch: issue the six coefficient loads of coefficient row r (row r+1 is fetched before row r
     // is consumed: software pipelining of the in-order warp); xpass: axis -1 synthesis of that row
-    // -> (L0, L1) from dA, (G0, G1) from dH for output columns 2m, 2m+1.
+    // -> (L0, L1) from dA, (G0, G1) from dH for output columns 2m, 2m+1.  All loads are
+    // unconditional on clamped addresses (the level buffers carry a few floats of slack), values
+    // outside the band are replaced by zero afterwards, so the compiler can hoist every load.
     auto fetch = [&](int r, float (&c)[6]) {
         const int gy = min(cy0 + r, Hl - 1);
         const unsigned o = (unsigned)(gy * pitch_l);
         if (pA) {
-            c[0] = pA[o];
-            c[1] = pA[o + o1];
-            c[2] = pA[o + o2];
+            const float* q = pA + o;
+            c[0] = q[0];
+            c[1] = q[1];
+            c[2] = q[2];
         } else {
             c[0] = c[1] = c[2] = 0.f;
         }
         if (pH) {
-            c[3] = pH[o];
-            c[4] = pH[o + o1];
-            c[5] = pH[o + o2];
+            const float* q = pH + o;
+            c[3] = q[0];
+            c[4] = q[1];
+            c[5] = q[2];
         } else {
             c[3] = c[4] = c[5] = 0.f;
         }
@@ -1003,9 +1044,11 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
     const bool v0ok = gx < Wo, v1ok = gx + 1 < Wo;
     const float one = ep.expm1 ? -1.0f : 1.0f;
     typedef RawPair<IN_T, VEC> Raw;
-    // per-lane image / output cursors (FINAL), advanced by one row at a time
-    const int gxc = min(gx, Wo - (VEC ? 2 : 1));
+    const int gxc = min(gx, Wo - (VEC ? 2 : 1));  // clamped columns (loads only)
     const int gx1c = min(gx + 1, Wo - 1);
+    const IN_T* img_z = FINAL ? img + (size_t)z * img_pstride : nullptr;
+    OUT_T* out_z = FINAL ? out + (size_t)z * img_pstride : nullptr;
+    float* outA_z = FINAL ? nullptr : outA + (size_t)z * pstride_o + gx;
     for (int my3 = 0; my3 < SY_TY / 2; my3 += 3) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1013,16 +1056,32 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
             float cc[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) cc[i] = cn[i];
-            if (my + 1 < SY_TY / 2) fetch(my + 3, cn);
-            // raw image pixels of the two output rows of this step (FINAL): issue the loads now,
-            // convert after the synthesis arithmetic
+            fetch(my + 3, cn);
+            // raw image pixels and dark / flat of the two output rows of this step (FINAL)
             Raw px[2];
+            float dk[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, ifl[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
+            unsigned pixc[2];
             if (FINAL) {
 #pragma unroll
                 for (int py = 0; py < 2; ++py) {
-                    const int gy = min(y0 + 2 * my + py, Ho - 1);
-                    const IN_T* rowp = img + (size_t)z * img_pstride + (unsigned)(gy * Wo);
+                    const int gyc = min(y0 + 2 * my + py, Ho - 1);
+                    pixc[py] = (unsigned)(gyc * Wo);
+                    const IN_T* rowp = img_z + pixc[py];
                     px[py].load(rowp + (VEC ? gxc : 0), VEC ? 0 : gxc, gx1c);
+                }
+                if (ep.shadow) {
+#pragma unroll
+                    for (int py = 0; py < 2; ++py) {
+                        if (VEC) {
+                            load_pair(ep.dark + pixc[py] + gxc, dk[py][0], dk[py][1]);
+                            load_pair(ep.inv_flat + pixc[py] + gxc, ifl[py][0], ifl[py][1]);
+                        } else {
+                            dk[py][0] = ep.dark[pixc[py] + gxc];
+                            dk[py][1] = ep.dark[pixc[py] + gx1c];
+                            ifl[py][0] = ep.inv_flat[pixc[py] + gxc];
+                            ifl[py][1] = ep.inv_flat[pixc[py] + gx1c];
+                        }
+                    }
                 }
             }
             // coefficient row my+2 enters the window; row r lives in slot r % 3
@@ -1041,36 +1100,21 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
                     v1 = fmaf(fl, L1[sl], v1);
                     v1 = fmaf(fh, G1[sl], v1);
                 }
-                if (gy >= Ho || !v0ok) continue;
+                const bool row_ok = (gy < Ho) && v0ok;
                 if (!FINAL) {
                     // pitch_o is a multiple of 4 and gx is even: the pair store stays inside the row
-                    float* o = outA + (size_t)z * pstride_o + (unsigned)(gy * pitch_o) + gx;
-                    store_pair(o, v0, v1);
+                    if (row_ok) store_pair(outA_z + (unsigned)(gy * pitch_o), v0, v1);
                 } else {
-                    const unsigned pix = (unsigned)(gy * Wo) + gx;
-                    const size_t gpix = (size_t)z * img_pstride + pix;
                     float xin0, xin1;
                     px[py].get(false, xin0, xin1);
                     // exp(log(1+x) + delta) + 1 == (1+x) * exp(delta) + 1   (filtering.py:175,222)
                     float r0 = fmaf(__fadd_rn(1.0f, xin0), DSTR_EXPF(v0), one);
                     float r1 = fmaf(__fadd_rn(1.0f, xin1), DSTR_EXPF(v1), one);
                     if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
-                        float dk0, dk1 = 0.f, if0, if1 = 1.f;
-                        if (VEC) {
-                            load_pair(ep.dark + pix, dk0, dk1);
-                            load_pair(ep.inv_flat + pix, if0, if1);
-                        } else {
-                            dk0 = ep.dark[pix];
-                            if0 = ep.inv_flat[pix];
-                            if (v1ok) {
-                                dk1 = ep.dark[pix + 1];
-                                if1 = ep.inv_flat[pix + 1];
-                            }
-                        }
-                        r0 = (r0 <= dk0) ? 0.f : (r0 - dk0);
-                        r1 = (r1 <= dk1) ? 0.f : (r1 - dk1);
-                        r0 *= if0;
-                        r1 *= if1;
+                        r0 = (r0 <= dk[py][0]) ? 0.f : (r0 - dk[py][0]);
+                        r1 = (r1 <= dk[py][1]) ? 0.f : (r1 - dk[py][1]);
+                        r0 *= ifl[py][0];
+                        r1 *= ifl[py][1];
                     }
                     if (sizeof(OUT_T) == 2 || ep.shadow) {
                         r0 = fminf(fmaxf(r0, 0.f), 65535.f);  // np.clip; the u16 conversion truncates
@@ -1080,11 +1124,14 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
                             r1 = truncf(r1);
                         }
                     }
-                    if (VEC) {
-                        store_pair(out + gpix, r0, r1);
-                    } else {
-                        store_one(out + gpix, r0);
-                        if (v1ok) store_one(out + gpix + 1, r1);
+                    if (row_ok) {
+                        OUT_T* o = out_z + pixc[py] + gx;  // gy < Ho: pixc is the unclamped row
+                        if (VEC) {
+                            store_pair(o, r0, r1);
+                        } else {
+                            store_one(o, r0);
+                            if (v1ok) store_one(o + 1, r1);
+                        }
                     }
                 }
             }
