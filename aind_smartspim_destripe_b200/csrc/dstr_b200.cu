@@ -877,7 +877,7 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
     }
 
     // ---- host buffers: three-stream pipeline over sub-chunks -----------------------------------------
-    int sub = ctx->subchunk > 0 ? ctx->subchunk : std::min(ctx->zcap, 16);
+    int sub = ctx->subchunk > 0 ? ctx->subchunk : std::min(ctx->zcap, 4);
     sub = std::min(sub, ctx->zcap);
     if (stack) sub = Z;
     rc = ensure_stage(ctx, sub);

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=2048)
     ap.add_argument("--batch-planes", type=int, default=0, help="planes per kernel launch (0 = engine default)")
     ap.add_argument("--unique-planes", type=int, default=16)
+    ap.add_argument("--subchunk", type=int, default=0, help="planes per H2D/compute/D2H pipeline stage in the e2e leg (0 = engine default)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU-baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -272,6 +273,8 @@ def run_b200(args):
         pin_in = E.PinnedBuffer((Z, H, W), np.uint16)
         pin_out = E.PinnedBuffer((Z, H, W), np.uint16)
         pin_in.array[...] = stack
+        if args.subchunk:
+            eng.set_subchunk(args.subchunk)
         for _ in range(2):
             eng.filter_chunk(pin_in.array, pn, cells=pc, out=pin_out.array, high_int=HIGH_INT, mode=mode, flags=flags)
         D.barrier()
