@@ -20,6 +20,7 @@ namespace {
 
 constexpr int kMaxLevels = 16;
 constexpr int kFilterTaps = 6;  // db3
+constexpr int kSideStreams = 3;
 
 std::mutex g_err_mutex;
 std::string g_last_error;
@@ -81,6 +82,9 @@ struct dstr_ctx {
     size_t stage_bytes = 0;
     int subchunk = 0;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_side[4] = {};                       // per-level hist/otsu/filter branches
+    cudaEvent_t ev_an[kMaxLevels + 1] = {}, ev_flt[kMaxLevels + 1] = {};
+    bool overlap = true;
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     float fg_half_thr = 384.f;
     double notch_eps = 1e-6;  // truncation tolerance of the hybrid notch operator (0 = dense)
@@ -433,210 +437,273 @@ void resolve_timers(dstr_ctx* ctx) {
 }
 
 template <int EPL>
-int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem,
-                  const DispatchParams& dp) {
-    CK(ctx, cudaFuncSetAttribute(filter_rows_kernel<EPL>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem, const DispatchParams& dp,
+                  cudaStream_t st) {
+    CK(ctx, cudaFuncSetAttribute(filter_rows_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((fa.Hl + FR_ROWS - 1) / FR_ROWS, Z);
-    filter_rows_kernel<EPL><<<grid, FR_THREADS, smem, ctx->s_comp>>>(fa, ctx->d_pstat, dp);
+    filter_rows_kernel<EPL><<<grid, FR_THREADS, smem, st>>>(fa, ctx->d_pstat, dp);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     return 0;
 }
 
-// Process z planes resident on the device (d_in -> d_out) on the compute stream.
+// Everything one chunk pass needs to launch its kernels.
+struct Pass {
+    dstr_ctx* ctx;
+    const void* d_in;
+    void* d_out;
+    int in_dtype, out_dtype, z, L, flags, stat_stride;
+    size_t level_stride;
+    DispatchParams dp;
+};
+
+int launch_analysis(const Pass& P, int l, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const int H = ctx->H, W = ctx->W, z = P.z;
+    const LevelGeom& gs = ctx->geom[l - 1];
+    const LevelGeom& go = ctx->geom[l];
+    const int cols_per_block = AN_OXW * AN_WX, rows_per_block = AN_TOY * AN_WY;
+    dim3 grid((go.W + cols_per_block - 1) / cols_per_block, (go.H + rows_per_block - 1) / rows_per_block, z);
+    LevelStat* ls = ctx->d_lstat + (size_t)(l - 1) * P.level_stride;
+    const bool stats = P.dp.mode == 1;
+#define LAUNCH_AN1(IN_T, ST, VEC)                                                                       \
+    analysis_kernel<IN_T, true, ST, VEC><<<grid, AN_THREADS, 0, st>>>(                                   \
+        (const IN_T*)P.d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W, go.pitch,     \
+        go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_half_thr)
+#define LAUNCH_AN1V(IN_T, ST)                \
+    do {                                     \
+        if (vec) LAUNCH_AN1(IN_T, ST, true); \
+        else LAUNCH_AN1(IN_T, ST, false);    \
+    } while (0)
+    // aligned two-element loads need an even width, pitch and plane stride
+    const bool vec = (gs.W % 2 == 0) && (gs.W >= 8) && (gs.H >= 8) && (gs.pitch % 2 == 0) && (gs.pstride % 2 == 0);
+    if (l == 1) {
+        if (P.in_dtype == DSTR_U16) {
+            if (stats) LAUNCH_AN1V(uint16_t, true);
+            else LAUNCH_AN1V(uint16_t, false);
+        } else {
+            if (stats) LAUNCH_AN1V(float, true);
+            else LAUNCH_AN1V(float, false);
+        }
+    } else if (vec) {
+        analysis_kernel<float, false, false, true><<<grid, AN_THREADS, 0, st>>>(
+            ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H, go.W, go.pitch,
+            go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+    } else {
+        analysis_kernel<float, false, false, false><<<grid, AN_THREADS, 0, st>>>(
+            ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H, go.W, go.pitch,
+            go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+    }
+#undef LAUNCH_AN1V
+#undef LAUNCH_AN1
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int launch_hist(const Pass& P, int l, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const LevelGeom& g = ctx->geom[l];
+    const int nblk = std::max(1, (g.H * (g.pitch / 4) + 2047) / 2048);  // ~8 quads per thread
+    dim3 grid(nblk, P.z);
+    hist_kernel<<<grid, 256, 0, st>>>(ctx->d_H[l], g.H, g.W, g.pitch, g.pstride,
+                                      ctx->d_lstat + (size_t)(l - 1) * P.level_stride, P.stat_stride);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Otsu thresholds of levels l0 .. l0+nl-1
+int launch_otsu(const Pass& P, int l0, int nl, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const bool stack = (P.flags & DSTR_FLAG_STACK_OTSU) != 0;
+    dim3 grid(stack ? 1 : P.z, nl);
+    otsu_kernel<<<grid, 32, 0, st>>>(ctx->d_lstat + (size_t)(l0 - 1) * P.level_stride, P.level_stride,
+                                     P.stat_stride, ctx->d_pstat, P.dp);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const LevelGeom& g = ctx->geom[l];
+    const TapTable& T = ctx->taps[l];
+    FilterLevelArgs fa;
+    fa.cH = ctx->d_H[l];
+    fa.Hl = g.H;
+    fa.Wl = g.W;
+    fa.pitch = g.pitch;
+    fa.pstride = g.pstride;
+    fa.lstat = ctx->d_lstat + (size_t)(l - 1) * P.level_stride;
+    fa.stat_stride = P.stat_stride;
+    fa.nt[0] = T.cfg[0].nt;
+    fa.nt[1] = T.cfg[1].nt;
+    fa.nh = g.W / 2;
+    fa.nhp8 = (fa.nh + 1 + 7) & ~7;
+    fa.n_pad8 = (g.W + 7) & ~7;
+    fa.ntap_e_max = std::max(fa.nt[0].ntap_e, fa.nt[1].ntap_e);
+    fa.ntap_o_max = std::max(fa.nt[0].ntap_o, fa.nt[1].ntap_o);
+    fa.Jpad_max = std::max(fa.nt[0].Jpad, fa.nt[1].Jpad);
+    fa.xlen_e_phys = (fa.nhp8 + fa.ntap_e_max) / 8 * 9;
+    fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
+    const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
+                                         (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
+                                         (size_t)FR_ROWS * fa.Jpad_max + (size_t)FR_ROWS * FR_ROWS * fa.Jpad_max);
+    if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
+    const int epl = (g.W + 31) / 32;
+    if (epl <= 2) return launch_filter<2>(ctx, fa, P.z, smem, P.dp, st);
+    if (epl <= 5) return launch_filter<5>(ctx, fa, P.z, smem, P.dp, st);
+    if (epl <= 9) return launch_filter<9>(ctx, fa, P.z, smem, P.dp, st);
+    if (epl <= 17) return launch_filter<17>(ctx, fa, P.z, smem, P.dp, st);
+    if (epl <= 33) return launch_filter<33>(ctx, fa, P.z, smem, P.dp, st);
+    if (epl <= 65) return launch_filter<65>(ctx, fa, P.z, smem, P.dp, st);
+    return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
+}
+
+// dA_{l-1} = idwt2(dA_l, dH_l)
+int launch_synth(const Pass& P, int l, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const LevelGeom& g = ctx->geom[l];
+    const LevelGeom& go = ctx->geom[l - 1];
+    EpilogueArgs ep0 = {};
+    dim3 grid((go.W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (go.H + SY_TY - 1) / SY_TY, P.z);
+    const float* dA = (l == P.L) ? nullptr : ctx->d_A[l];
+    synth_kernel<false, float, float, false><<<grid, SY_THREADS, 0, st>>>(
+        dA, ctx->d_H[l], g.H, g.W, g.pitch, g.pstride, ctx->d_A[l - 1], go.H, go.W, go.pitch, go.pstride, nullptr,
+        nullptr, 0, ep0);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int launch_final(const Pass& P, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const int H = ctx->H, W = ctx->W, L = P.L;
+    EpilogueArgs ep;
+    ep.inv_flat = ctx->d_flat;  // stored as the correctly rounded reciprocal
+    ep.dark = ctx->d_dark;
+    ep.shadow = (P.flags & DSTR_FLAG_SHADOW) ? 1 : 0;
+    ep.expm1 = (P.flags & DSTR_FLAG_EXPM1) ? 1 : 0;
+    const LevelGeom& g = ctx->geom[L > 0 ? 1 : 0];
+    const float* dA = (L >= 2) ? ctx->d_A[1] : nullptr;
+    const float* dH = (L >= 1) ? ctx->d_H[1] : nullptr;
+    dim3 grid((W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (H + SY_TY - 1) / SY_TY, P.z);
+    const size_t ps = (size_t)H * W;
+#define LAUNCH_FINAL_V(IN_T, OUT_T, VEC)                                                                   \
+    synth_kernel<true, IN_T, OUT_T, VEC><<<grid, SY_THREADS, 0, st>>>(                                     \
+        dA, dH, g.H, g.W, g.pitch, g.pstride, nullptr, H, W, W, ps, (const IN_T*)P.d_in, (OUT_T*)P.d_out, \
+        ps, ep)
+#define LAUNCH_FINAL(IN_T, OUT_T)                    \
+    do {                                             \
+        if (vecf) LAUNCH_FINAL_V(IN_T, OUT_T, true); \
+        else LAUNCH_FINAL_V(IN_T, OUT_T, false);     \
+    } while (0)
+    const bool vecf = (W % 2 == 0) && (W >= 2) && (ps % 2 == 0);
+    if (P.in_dtype == DSTR_U16 && P.out_dtype == DSTR_U16) LAUNCH_FINAL(uint16_t, uint16_t);
+    else if (P.in_dtype == DSTR_U16 && P.out_dtype == DSTR_F32) LAUNCH_FINAL(uint16_t, float);
+    else if (P.in_dtype == DSTR_F32 && P.out_dtype == DSTR_U16) LAUNCH_FINAL(float, uint16_t);
+    else LAUNCH_FINAL(float, float);
+#undef LAUNCH_FINAL_V
+#undef LAUNCH_FINAL
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+#define RC(call)             \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+// Process z planes resident on the device (d_in -> d_out).
+//
+// Dependency graph of one pass:  A_1 -> A_2 -> ... -> A_L (analysis chain);  per level
+// A_l -> hist_l -> otsu_l -> filter_l;  synthesis chain S_L -> ... -> S_2 -> final, where S_l needs
+// filter_l.  The per-level branches are independent of the analysis chain below them, so in the
+// normal mode they run on side streams (the long level-1 row filter overlaps the whole deep
+// pyramid); the compute stream carries the two chains and joins the branches by events.  With
+// profiling or a debug stop the pass is issued stage by stage on the compute stream alone.
 int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, int out_dtype, int z,
                    const dstr_params& cells, const dstr_params& no_cells, float high_int, int mode,
                    int flags, int L) {
     cudaStream_t st = ctx->s_comp;
-    const int H = ctx->H, W = ctx->W;
-    const bool stack = (flags & DSTR_FLAG_STACK_OTSU) != 0;
-    const int stat_stride = stack ? 0 : 1;
-    const size_t level_stride = (size_t)ctx->zcap;
+    Pass P;
+    P.ctx = ctx;
+    P.d_in = d_in;
+    P.d_out = d_out;
+    P.in_dtype = in_dtype;
+    P.out_dtype = out_dtype;
+    P.z = z;
+    P.L = L;
+    P.flags = flags;
+    P.stat_stride = (flags & DSTR_FLAG_STACK_OTSU) ? 0 : 1;
+    P.level_stride = (size_t)ctx->zcap;
+    P.dp.max_thr_cells = cells.max_threshold;
+    P.dp.max_thr_nocells = no_cells.max_threshold;
+    P.dp.high_int = high_int;
+    P.dp.mode = (mode == DSTR_MODE_DISPATCH) ? 1 : 0;
     ctx->last_levels = L;
     ctx->last_z = z;
 
-    DispatchParams dp;
-    dp.max_thr_cells = cells.max_threshold;
-    dp.max_thr_nocells = no_cells.max_threshold;
-    dp.high_int = high_int;
-    dp.mode = (mode == DSTR_MODE_DISPATCH) ? 1 : 0;
-
     ScopedTimer t_all(ctx, 7);
-    if (L > 0) {
-        CK(ctx, cudaMemsetAsync(ctx->d_lstat, 0, sizeof(LevelStat) * level_stride * ctx->Lmax, st));
-    }
+    if (L > 0) CK(ctx, cudaMemsetAsync(ctx->d_lstat, 0, sizeof(LevelStat) * P.level_stride * ctx->Lmax, st));
     CK(ctx, cudaMemsetAsync(ctx->d_pstat, 0, sizeof(PlaneStat) * ctx->zcap, st));
 
-    if (L == 0 && dp.mode == 1) {
-        // dispatch is irrelevant with zero levels (both configs give x + 2)
-    }
-
-    // ---- analysis -----------------------------------------------------------------------------
-    for (int l = 1; l <= L; ++l) {
-        ScopedTimer t(ctx, l == 1 ? 0 : 1);
-        const LevelGeom& gs = ctx->geom[l - 1];
-        const LevelGeom& go = ctx->geom[l];
-        const int cols_per_block = AN_OXW * AN_WX, rows_per_block = AN_TOY * AN_WY;
-        dim3 grid((go.W + cols_per_block - 1) / cols_per_block, (go.H + rows_per_block - 1) / rows_per_block, z);
-        LevelStat* ls = ctx->d_lstat + (size_t)(l - 1) * level_stride;
-        const bool stats = dp.mode == 1;
-#define LAUNCH_AN1(IN_T, ST, VEC)                                                                     \
-    analysis_kernel<IN_T, true, ST, VEC><<<grid, AN_THREADS, 0, st>>>(                                 \
-        (const IN_T*)d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W, go.pitch,     \
-        go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr)
-#define LAUNCH_AN1V(IN_T, ST)        \
-    do {                             \
-        if (vec) LAUNCH_AN1(IN_T, ST, true); \
-        else LAUNCH_AN1(IN_T, ST, false);    \
-    } while (0)
-        // aligned two-element loads need an even width, pitch and plane stride
-        const bool vec = (gs.W % 2 == 0) && (gs.W >= 8) && (gs.H >= 8) && (gs.pitch % 2 == 0) && (gs.pstride % 2 == 0);
-        if (l == 1) {
-            if (in_dtype == DSTR_U16) {
-                if (stats) LAUNCH_AN1V(uint16_t, true);
-                else LAUNCH_AN1V(uint16_t, false);
-            } else {
-                if (stats) LAUNCH_AN1V(float, true);
-                else LAUNCH_AN1V(float, false);
+    const bool staged = ctx->profiling || ctx->debug_stop != DSTR_STAGE_NONE || !ctx->overlap;
+    if (staged) {
+        for (int l = 1; l <= L; ++l) {
+            ScopedTimer t(ctx, l == 1 ? 0 : 1);
+            RC(launch_analysis(P, l, st));
+        }
+        if (ctx->debug_stop == DSTR_STAGE_ANALYSIS) return 0;
+        if (L > 0) {
+            {
+                ScopedTimer t(ctx, 2);
+                for (int l = 1; l <= L; ++l) RC(launch_hist(P, l, st));
             }
-        } else if (vec) {
-            analysis_kernel<float, false, false, true><<<grid, AN_THREADS, 0, st>>>(
-                ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H,
-                go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
-        } else {
-            analysis_kernel<float, false, false, false><<<grid, AN_THREADS, 0, st>>>(
-                ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H,
-                go.W, go.pitch, go.pstride, ls, stat_stride, ctx->d_pstat, ctx->fg_half_thr);
-        }
-#undef LAUNCH_AN1V
-#undef LAUNCH_AN1
-        ctx->launches++;
-        CK(ctx, cudaGetLastError());
-    }
-    if (ctx->debug_stop == DSTR_STAGE_ANALYSIS) return 0;
-
-    if (L > 0) {
-        // ---- histogram + Otsu ------------------------------------------------------------------
-        {
-            ScopedTimer t(ctx, 2);
-            for (int l = 1; l <= L; ++l) {
-                const LevelGeom& g = ctx->geom[l];
-                const int nblk = std::max(1, (g.H * (g.pitch / 4) + 2047) / 2048);  // ~8 quads per thread
-                dim3 grid(nblk, z);
-                hist_kernel<<<grid, 256, 0, st>>>(ctx->d_H[l], g.H, g.W, g.pitch, g.pstride,
-                                                  ctx->d_lstat + (size_t)(l - 1) * level_stride,
-                                                  stat_stride);
-                ctx->launches++;
-                CK(ctx, cudaGetLastError());
+            {
+                ScopedTimer t(ctx, 3);
+                RC(launch_otsu(P, 1, L, st));
             }
-        }
-        {
-            ScopedTimer t(ctx, 3);
-            dim3 grid(stack ? 1 : z, L);
-            otsu_kernel<<<grid, 32, 0, st>>>(ctx->d_lstat, level_stride, stat_stride, ctx->d_pstat,
-                                             dp);
-            ctx->launches++;
-            CK(ctx, cudaGetLastError());
-        }
-        if (ctx->debug_stop == DSTR_STAGE_OTSU) return 0;
-
-        // ---- row filter ------------------------------------------------------------------------
-        {
-            ScopedTimer t(ctx, 4);
-            for (int l = 1; l <= L; ++l) {
-                const LevelGeom& g = ctx->geom[l];
-                const TapTable& T = ctx->taps[l];
-                FilterLevelArgs fa;
-                fa.cH = ctx->d_H[l];
-                fa.Hl = g.H;
-                fa.Wl = g.W;
-                fa.pitch = g.pitch;
-                fa.pstride = g.pstride;
-                fa.lstat = ctx->d_lstat + (size_t)(l - 1) * level_stride;
-                fa.stat_stride = stat_stride;
-                fa.nt[0] = T.cfg[0].nt;
-                fa.nt[1] = T.cfg[1].nt;
-                fa.nh = g.W / 2;
-                fa.nhp8 = (fa.nh + 1 + 7) & ~7;
-                fa.n_pad8 = (g.W + 7) & ~7;
-                fa.ntap_e_max = std::max(fa.nt[0].ntap_e, fa.nt[1].ntap_e);
-                fa.ntap_o_max = std::max(fa.nt[0].ntap_o, fa.nt[1].ntap_o);
-                fa.Jpad_max = std::max(fa.nt[0].Jpad, fa.nt[1].Jpad);
-                fa.xlen_e_phys = (fa.nhp8 + fa.ntap_e_max) / 8 * 9;
-                fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
-                const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
-                                                     (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
-                                                     (size_t)FR_ROWS * fa.Jpad_max +
-                                                     (size_t)FR_ROWS * FR_ROWS * fa.Jpad_max);
-                if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
-                const int epl = (g.W + 31) / 32;
-                int rc;
-                if (epl <= 2) rc = launch_filter<2>(ctx, fa, z, smem, dp);
-                else if (epl <= 5) rc = launch_filter<5>(ctx, fa, z, smem, dp);
-                else if (epl <= 9) rc = launch_filter<9>(ctx, fa, z, smem, dp);
-                else if (epl <= 17) rc = launch_filter<17>(ctx, fa, z, smem, dp);
-                else if (epl <= 33) rc = launch_filter<33>(ctx, fa, z, smem, dp);
-                else if (epl <= 65) rc = launch_filter<65>(ctx, fa, z, smem, dp);
-                else return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
-                if (rc) return rc;
+            if (ctx->debug_stop == DSTR_STAGE_OTSU) return 0;
+            {
+                ScopedTimer t(ctx, 4);
+                for (int l = 1; l <= L; ++l) RC(launch_filter_level(P, l, st));
             }
-        }
-        if (ctx->debug_stop == DSTR_STAGE_FILTER) return 0;
-
-        // ---- synthesis of the deltas, levels L..2 ----------------------------------------------
-        {
-            ScopedTimer t(ctx, 5);
-            EpilogueArgs ep0 = {};
-            for (int l = L; l >= 2; --l) {
-                const LevelGeom& g = ctx->geom[l];
-                const LevelGeom& go = ctx->geom[l - 1];
-                dim3 grid((go.W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (go.H + SY_TY - 1) / SY_TY, z);
-                const float* dA = (l == L) ? nullptr : ctx->d_A[l];
-                synth_kernel<false, float, float, false><<<grid, SY_THREADS, 0, st>>>(
-                    dA, ctx->d_H[l], g.H, g.W, g.pitch, g.pstride, ctx->d_A[l - 1], go.H, go.W,
-                    go.pitch, go.pstride, nullptr, nullptr, 0, ep0);
-                ctx->launches++;
-                CK(ctx, cudaGetLastError());
+            if (ctx->debug_stop == DSTR_STAGE_FILTER) return 0;
+            {
+                ScopedTimer t(ctx, 5);
+                for (int l = L; l >= 2; --l) RC(launch_synth(P, l, st));
             }
+            if (ctx->debug_stop == DSTR_STAGE_SYNTH) return 0;
         }
-        if (ctx->debug_stop == DSTR_STAGE_SYNTH) return 0;
-    }
-
-    // ---- final level + inverse log + epilogue ------------------------------------------------------
-    {
         ScopedTimer t(ctx, 6);
-        EpilogueArgs ep;
-        ep.inv_flat = ctx->d_flat;  // stored as the correctly rounded reciprocal
-        ep.dark = ctx->d_dark;
-        ep.shadow = (flags & DSTR_FLAG_SHADOW) ? 1 : 0;
-        ep.expm1 = (flags & DSTR_FLAG_EXPM1) ? 1 : 0;
-        const LevelGeom& g = ctx->geom[L > 0 ? 1 : 0];
-        const float* dA = (L >= 2) ? ctx->d_A[1] : nullptr;
-        const float* dH = (L >= 1) ? ctx->d_H[1] : nullptr;
-        dim3 grid((W + SY_TX * SY_WARPS - 1) / (SY_TX * SY_WARPS), (H + SY_TY - 1) / SY_TY, z);
-        const size_t ps = (size_t)H * W;
-#define LAUNCH_FINAL_V(IN_T, OUT_T, VEC)                                                               \
-    synth_kernel<true, IN_T, OUT_T, VEC><<<grid, SY_THREADS, 0, st>>>(                                 \
-        dA, dH, g.H, g.W, g.pitch, g.pstride, nullptr, H, W, W, ps, (const IN_T*)d_in, (OUT_T*)d_out,  \
-        ps, ep)
-#define LAUNCH_FINAL(IN_T, OUT_T)                 \
-    do {                                          \
-        if (vecf) LAUNCH_FINAL_V(IN_T, OUT_T, true);  \
-        else LAUNCH_FINAL_V(IN_T, OUT_T, false);      \
-    } while (0)
-        const bool vecf = (W % 2 == 0) && (W >= 2) && (ps % 2 == 0);
-        if (in_dtype == DSTR_U16 && out_dtype == DSTR_U16) LAUNCH_FINAL(uint16_t, uint16_t);
-        else if (in_dtype == DSTR_U16 && out_dtype == DSTR_F32) LAUNCH_FINAL(uint16_t, float);
-        else if (in_dtype == DSTR_F32 && out_dtype == DSTR_U16) LAUNCH_FINAL(float, uint16_t);
-        else LAUNCH_FINAL(float, float);
-#undef LAUNCH_FINAL_V
-#undef LAUNCH_FINAL
-        ctx->launches++;
-        CK(ctx, cudaGetLastError());
+        RC(launch_final(P, st));
+        return 0;
     }
+
+    // ---- overlapped issue ---------------------------------------------------------------------------
+    for (int l = 1; l <= L; ++l) {
+        RC(launch_analysis(P, l, st));
+        CK(ctx, cudaEventRecord(ctx->ev_an[l], st));
+        cudaStream_t side = ctx->s_side[(l - 1) % kSideStreams];
+        CK(ctx, cudaStreamWaitEvent(side, ctx->ev_an[l], 0));
+        RC(launch_hist(P, l, side));
+        RC(launch_otsu(P, l, 1, side));
+        RC(launch_filter_level(P, l, side));
+        CK(ctx, cudaEventRecord(ctx->ev_flt[l], side));
+    }
+    for (int l = L; l >= 2; --l) {
+        CK(ctx, cudaStreamWaitEvent(st, ctx->ev_flt[l], 0));
+        RC(launch_synth(P, l, st));
+    }
+    if (L >= 1) CK(ctx, cudaStreamWaitEvent(st, ctx->ev_flt[1], 0));
+    RC(launch_final(P, st));
     return 0;
 }
+#undef RC
 
 size_t dtype_size(int dt) { return dt == DSTR_U16 ? 2 : 4; }
 
@@ -747,7 +814,19 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
     if (ctx->Lmax > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lmax * max_planes));
     CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));
     CKC(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    {
+        // the compute stream carries the dependency chains: give it the highest priority so that
+        // its short kernels are not queued behind the long row filters of the side streams
+        int prio_lo = 0, prio_hi = 0;
+        CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CKC(cudaStreamCreateWithPriority(&ctx->s_comp, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < kSideStreams; ++i)
+            CKC(cudaStreamCreateWithPriority(&ctx->s_side[i], cudaStreamNonBlocking, prio_lo));
+        for (int l = 0; l <= kMaxLevels; ++l) {
+            CKC(cudaEventCreateWithFlags(&ctx->ev_an[l], cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&ctx->ev_flt[l], cudaEventDisableTiming));
+        }
+    }
     CKC(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CKC(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
@@ -789,6 +868,15 @@ int dstr_destroy(dstr_ctx* ctx) {
         cudaEventDestroy(sp.b);
     }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < kSideStreams; ++i)
+        if (ctx->s_side[i]) {
+            cudaStreamSynchronize(ctx->s_side[i]);
+            cudaStreamDestroy(ctx->s_side[i]);
+        }
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        if (ctx->ev_an[l]) cudaEventDestroy(ctx->ev_an[l]);
+        if (ctx->ev_flt[l]) cudaEventDestroy(ctx->ev_flt[l]);
+    }
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -1138,6 +1226,12 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
         const int tm = n - t;
         if (t != 0 && tm != t) y[tm] = ye - yo;
     }
+    return 0;
+}
+
+int dstr_set_overlap(dstr_ctx* ctx, int enabled) {
+    if (!ctx) return DSTR_E_ARG;
+    ctx->overlap = enabled != 0;
     return 0;
 }
 

@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
             "dstr_set_debug_stop": (C.c_int, [vp, C.c_int]),
             "dstr_debug_fetch": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_uint64]),
             "dstr_set_subchunk": (C.c_int, [vp, C.c_int]),
+            "dstr_set_overlap": (C.c_int, [vp, C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = (
     "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
-    "dstr_debug_fetch dstr_set_subchunk"
+    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap"
 ).split()
 
 
@@ -404,6 +405,9 @@ class DestripeEngine:
 
     def set_notch_tolerance(self, eps: float):
         self._ck(self.lib.dstr_set_notch_tolerance(self.ctx, float(eps)), "dstr_set_notch_tolerance")
+
+    def set_overlap(self, enabled: bool):
+        self._ck(self.lib.dstr_set_overlap(self.ctx, 1 if enabled else 0), "dstr_set_overlap")
 
     def set_debug_stop(self, stage: int):
         self._ck(self.lib.dstr_set_debug_stop(self.ctx, int(stage)), "dstr_set_debug_stop")

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--unique-planes", type=int, default=16)
     ap.add_argument("--subchunk", type=int, default=0, help="planes per H2D/compute/D2H pipeline stage in the e2e leg (0 = engine default)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU-baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-overlap", action="store_true", help="issue every kernel on one stream in stage order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -207,6 +208,8 @@ def run_b200(args):
                               cells_every=2 if args.workload == "c3" else 0)
     batch = args.batch_planes or min(Z, 128)
     eng = E.DestripeEngine(H, W, max_planes=batch, device=device)
+    if args.no_overlap:
+        eng.set_overlap(False)
     pn, pc = E.make_params(NO_CELLS), None
     mode, flags = E.MODE_LOGSPACE, 0
     if args.workload == "c3":

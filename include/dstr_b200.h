@@ -155,6 +155,9 @@ int dstr_get_timers(dstr_ctx* ctx, double* ms_out /*[DSTR_NUM_TIMERS]*/, uint64_
 int dstr_reset_timers(dstr_ctx* ctx);
 int dstr_set_debug_stop(dstr_ctx* ctx, int stage);
 int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_t host_bytes);
+/* 1 (default): the per-level histogram / Otsu / row-filter branches run on side streams next to
+ * the analysis and synthesis chains; 0: every kernel on the compute stream in stage order */
+int dstr_set_overlap(dstr_ctx* ctx, int enabled);
 /* sub-chunk size (planes) used when streaming host buffers; 0 restores the default */
 int dstr_set_subchunk(dstr_ctx* ctx, int planes);
 
