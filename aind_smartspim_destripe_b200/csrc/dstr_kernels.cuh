@@ -1031,12 +1031,13 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
     };
 
     float L0[3], L1[3], G0[3], G1[3];
-    float cn[6];  // coefficient row in flight
+    float cn[6], cn2[6];  // coefficient rows in flight (two steps ahead: more bytes in flight per warp)
     {
         float ca[6], cb[6];
         fetch(0, ca);
         fetch(1, cb);
         fetch(2, cn);
+        fetch(3, cn2);
         xpass(0, ca, L0[0], L1[0], G0[0], G1[0]);
         xpass(1, cb, L0[1], L1[1], G0[1], G1[1]);
     }
@@ -1055,8 +1056,11 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
             const int my = my3 + k;
             float cc[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) cc[i] = cn[i];
-            fetch(my + 3, cn);
+            for (int i = 0; i < 6; ++i) {
+                cc[i] = cn[i];
+                cn[i] = cn2[i];
+            }
+            fetch(my + 4, cn2);
             // raw image pixels and dark / flat of the two output rows of this step (FINAL)
             Raw px[2];
             float dk[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, ifl[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
