@@ -80,6 +80,10 @@ struct dstr_ctx {
     void* d_in[2] = {nullptr, nullptr};
     void* d_out[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
+    // optional fused pyramid outputs (levels 1 and 2) of the chunk being destriped
+    void* pyr_out[2] = {nullptr, nullptr};
+    uint16_t* d_pyr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [level][buffer]
+    size_t pyr_bytes = 0;
     int subchunk = 0;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaStream_t s_side[4] = {};                       // per-level hist/otsu/filter branches
@@ -705,6 +709,17 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
 }
 #undef RC
 
+int launch_downscale(dstr_ctx* ctx, const uint16_t* in, int Z, int H, int W, uint16_t* out, cudaStream_t st) {
+    const int Zo = Z / 2, Ho = H / 2, Wo = W / 2;
+    const size_t n = (size_t)Zo * Ho * Wo;
+    if (n == 0) return 0;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 32);
+    downscale2x_kernel<<<blocks, 256, 0, st>>>(in, Z, H, W, out, Zo, Ho, Wo);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
 size_t dtype_size(int dt) { return dt == DSTR_U16 ? 2 : 4; }
 
 bool is_device_ptr(const void* p) {
@@ -731,6 +746,48 @@ int ensure_stage(dstr_ctx* ctx, int planes) {
     }
     ctx->stage_bytes = need;
     return 0;
+}
+
+int ensure_pyramid_stage(dstr_ctx* ctx, int planes) {
+    const size_t need = (size_t)(planes / 2 + 1) * (ctx->H / 2 + 1) * (ctx->W / 2 + 1) * sizeof(uint16_t);
+    if (ctx->pyr_bytes >= need) return 0;
+    for (int l = 0; l < 2; ++l)
+        for (int b = 0; b < 2; ++b) {
+            if (ctx->d_pyr[l][b]) cudaFree(ctx->d_pyr[l][b]);
+            ctx->d_pyr[l][b] = nullptr;
+        }
+    ctx->pyr_bytes = 0;
+    for (int l = 0; l < 2; ++l)
+        for (int b = 0; b < 2; ++b) CK(ctx, cudaMalloc(&ctx->d_pyr[l][b], need));
+    ctx->pyr_bytes = need;
+    return 0;
+}
+
+// Fused pyramid levels of a destriped batch that is still resident (next-row f3): level 1 =
+// 2x2x2 windowed mean of the uint16 output, level 2 = the same of level 1.  z0 is a multiple of 4.
+// Returns through *h1 / *h2 the device staging pointers that still have to be copied to host
+// targets (nullptr when the kernel wrote the target directly).
+int emit_pyramid(dstr_ctx* ctx, const uint16_t* d_out, int z0, int zn, int b, cudaStream_t st,
+                 uint16_t** h1, uint16_t** h2) {
+    *h1 = *h2 = nullptr;
+    const int H1 = ctx->H / 2, W1 = ctx->W / 2, H2 = H1 / 2, W2 = W1 / 2;
+    if (!ctx->pyr_out[0]) return 0;
+    uint16_t* t1 = (uint16_t*)ctx->pyr_out[0] + (size_t)(z0 / 2) * H1 * W1;
+    uint16_t* w1 = t1;
+    if (!is_device_ptr(ctx->pyr_out[0])) {
+        w1 = ctx->d_pyr[0][b];
+        *h1 = w1;
+    }
+    int rc = launch_downscale(ctx, d_out, zn, ctx->H, ctx->W, w1, st);
+    if (rc) return rc;
+    if (!ctx->pyr_out[1]) return 0;
+    uint16_t* t2 = (uint16_t*)ctx->pyr_out[1] + (size_t)(z0 / 4) * H2 * W2;
+    uint16_t* w2 = t2;
+    if (!is_device_ptr(ctx->pyr_out[1])) {
+        w2 = ctx->d_pyr[1][b];
+        *h2 = w2;
+    }
+    return launch_downscale(ctx, w1, zn / 2, H1, W1, w2, st);
 }
 
 }  // namespace
@@ -852,6 +909,9 @@ int dstr_destroy(dstr_ctx* ctx) {
         for (int c = 0; c < 2; ++c)
             if (ctx->taps[l].cfg[c].d_buf) cudaFree(ctx->taps[l].cfg[c].d_buf);
     }
+    for (int l = 0; l < 2; ++l)
+        for (int b2 = 0; b2 < 2; ++b2)
+            if (ctx->d_pyr[l][b2]) cudaFree(ctx->d_pyr[l][b2]);
     if (ctx->d_lstat) cudaFree(ctx->d_lstat);
     if (ctx->d_pstat) cudaFree(ctx->d_pstat);
     if (ctx->d_flat) cudaFree(ctx->d_flat);
@@ -948,14 +1008,33 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
     if (stack && Z > ctx->zcap)
         return fail(ctx, DSTR_E_SHAPE, "stack-wide Otsu needs the whole chunk within max_planes");
 
+    const bool pyramid = ctx->pyr_out[0] != nullptr;
+    if (pyramid) {
+        if (out_dtype != DSTR_U16) return fail(ctx, DSTR_E_ARG, "pyramid outputs need a uint16 chunk output");
+        if (ctx->zcap < 4) return fail(ctx, DSTR_E_STATE, "pyramid outputs need max_planes >= 4");
+        int rcp = ensure_pyramid_stage(ctx, ctx->zcap);
+        if (rcp) return rcp;
+    }
     int rc = 0;
     if (in_dev && out_dev) {
-        for (int z0 = 0; z0 < Z; z0 += ctx->zcap) {
-            const int zn = std::min(ctx->zcap, Z - z0);
+        const int zstep = pyramid ? (ctx->zcap & ~3) : ctx->zcap;
+        for (int z0 = 0; z0 < Z; z0 += zstep) {
+            const int zn = std::min(zstep, Z - z0);
             rc = process_device(ctx, (const char*)in + (size_t)z0 * in_pb, in_dtype,
                                 (char*)out + (size_t)z0 * out_pb, out_dtype, zn, pc, pn, high_int, mode,
                                 flags, L);
             if (rc) return rc;
+            if (pyramid) {
+                uint16_t *h1, *h2;
+                rc = emit_pyramid(ctx, (const uint16_t*)((char*)out + (size_t)z0 * out_pb), z0, zn, 0, ctx->s_comp, &h1, &h2);
+                if (rc) return rc;
+                const int H1 = ctx->H / 2, W1 = ctx->W / 2;
+                if (h1) CK(ctx, cudaMemcpyAsync((uint16_t*)ctx->pyr_out[0] + (size_t)(z0 / 2) * H1 * W1, h1,
+                                                sizeof(uint16_t) * (size_t)(zn / 2) * H1 * W1, cudaMemcpyDeviceToHost, ctx->s_comp));
+                if (h2) CK(ctx, cudaMemcpyAsync((uint16_t*)ctx->pyr_out[1] + (size_t)(z0 / 4) * (H1 / 2) * (W1 / 2), h2,
+                                                sizeof(uint16_t) * (size_t)(zn / 4) * (H1 / 2) * (W1 / 2), cudaMemcpyDeviceToHost, ctx->s_comp));
+                if (h1 || h2) CK(ctx, cudaStreamSynchronize(ctx->s_comp));  // staging buffer 0 is reused by the next batch
+            }
         }
         if (!(flags & DSTR_FLAG_NO_SYNC) || ctx->profiling) {
             CK(ctx, cudaStreamSynchronize(ctx->s_comp));
@@ -967,6 +1046,7 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
     // ---- host buffers: three-stream pipeline over sub-chunks -----------------------------------------
     int sub = ctx->subchunk > 0 ? ctx->subchunk : std::min(ctx->zcap, 4);
     sub = std::min(sub, ctx->zcap);
+    if (pyramid) sub = std::max(4, sub & ~3);
     if (stack) sub = Z;
     rc = ensure_stage(ctx, sub);
     if (rc) return rc;
@@ -986,16 +1066,27 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
             CK(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
             dsrc = ctx->d_in[b];
         }
-        if (!out_dev) {
+        if (!out_dev || pyramid) {
             if (it >= 2) CK(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[b], 0));
-            ddst = ctx->d_out[b];
         }
+        if (!out_dev) ddst = ctx->d_out[b];
         rc = process_device(ctx, dsrc, in_dtype, ddst, out_dtype, zn, pc, pn, high_int, mode, flags, L);
         if (rc) return rc;
+        uint16_t *h1 = nullptr, *h2 = nullptr;
+        if (pyramid) {
+            rc = emit_pyramid(ctx, (const uint16_t*)ddst, z0, zn, b, ctx->s_comp, &h1, &h2);
+            if (rc) return rc;
+        }
         CK(ctx, cudaEventRecord(ctx->ev_comp[b], ctx->s_comp));
-        if (!out_dev) {
+        if (!out_dev || h1 || h2) {
             CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[b], 0));
-            CK(ctx, cudaMemcpyAsync(dst, ctx->d_out[b], out_pb * zn, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (!out_dev)
+                CK(ctx, cudaMemcpyAsync(dst, ctx->d_out[b], out_pb * zn, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            const int H1 = ctx->H / 2, W1 = ctx->W / 2;
+            if (h1) CK(ctx, cudaMemcpyAsync((uint16_t*)ctx->pyr_out[0] + (size_t)(z0 / 2) * H1 * W1, h1,
+                                            sizeof(uint16_t) * (size_t)(zn / 2) * H1 * W1, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (h2) CK(ctx, cudaMemcpyAsync((uint16_t*)ctx->pyr_out[1] + (size_t)(z0 / 4) * (H1 / 2) * (W1 / 2), h2,
+                                            sizeof(uint16_t) * (size_t)(zn / 4) * (H1 / 2) * (W1 / 2), cudaMemcpyDeviceToHost, ctx->s_d2h));
             CK(ctx, cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
         }
     }
@@ -1227,6 +1318,42 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
         if (t != 0 && tm != t) y[tm] = ye - yo;
     }
     return 0;
+}
+
+int dstr_set_pyramid_outputs(dstr_ctx* ctx, void* level1, void* level2) {
+    if (!ctx) return DSTR_E_ARG;
+    if (!level1 && level2) return fail(ctx, DSTR_E_ARG, "level 2 needs level 1");
+    ctx->pyr_out[0] = level1;
+    ctx->pyr_out[1] = level2;
+    return 0;
+}
+
+int dstr_downscale2x(dstr_ctx* ctx, const uint16_t* in, int Z, int H, int W, uint16_t* out) {
+    if (!ctx || !in || !out || Z < 2 || H < 2 || W < 2) return fail(ctx, DSTR_E_ARG, "dstr_downscale2x: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n_in = (size_t)Z * H * W, n_out = (size_t)(Z / 2) * (H / 2) * (W / 2);
+    const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
+    uint16_t *d_in = (uint16_t*)in, *d_out = out;
+    int rc = 0;
+    if (!in_dev) {
+        CK(ctx, cudaMalloc(&d_in, n_in * 2));
+        cudaError_t e = cudaMemcpyAsync(d_in, in, n_in * 2, cudaMemcpyHostToDevice, ctx->s_comp);
+        if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e));
+    }
+    if (!rc && !out_dev) {
+        cudaError_t e = cudaMalloc(&d_out, n_out * 2);
+        if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e));
+    }
+    if (!rc) rc = launch_downscale(ctx, d_in, Z, H, W, d_out, ctx->s_comp);
+    if (!rc && !out_dev) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, n_out * 2, cudaMemcpyDeviceToHost, ctx->s_comp);
+        if (e != cudaSuccess) rc = fail(ctx, (int)e, cudaGetErrorString(e));
+    }
+    cudaError_t es = cudaStreamSynchronize(ctx->s_comp);
+    if (!rc && es != cudaSuccess) rc = fail(ctx, (int)es, cudaGetErrorString(es));
+    if (!in_dev && d_in) cudaFree(d_in);
+    if (!out_dev && d_out) cudaFree(d_out);
+    return rc;
 }
 
 int dstr_set_overlap(dstr_ctx* ctx, int enabled) {

@@ -1160,4 +1160,27 @@ flatfield_kernel(const float* __restrict__ img, const float* __restrict__ flat,
     }
 }
 
+// 2x2x2 windowed mean of uint16 volumes with truncation (xarray_multiscale.windowed_mean +
+// preserve_dtype, zarr_destriper.py:399-405): out = floor(sum of 8 / 8); odd trailing planes, rows
+// and columns are cropped.  One thread per output voxel pair along x when Wo is even.
+__global__ void __launch_bounds__(256)
+downscale2x_kernel(const unsigned short* __restrict__ in, int Z, int H, int W,
+                   unsigned short* __restrict__ out, int Zo, int Ho, int Wo) {
+    const size_t n = (size_t)Zo * Ho * Wo;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int x = (int)(i % Wo);
+        const size_t t = i / Wo;
+        const int y = (int)(t % Ho), z = (int)(t / Ho);
+        unsigned sum = 0;
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const unsigned short* p = in + ((size_t)(2 * z + dz) * H + (2 * y + dy)) * W + 2 * x;
+                sum += (unsigned)p[0] + (unsigned)p[1];
+            }
+        out[i] = (unsigned short)(sum >> 3);
+    }
+}
+
 }  // namespace dstr

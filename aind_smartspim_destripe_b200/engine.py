@@ -102,6 +102,8 @@ def load_library() -> C.CDLL:
             "dstr_debug_fetch": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_uint64]),
             "dstr_set_subchunk": (C.c_int, [vp, C.c_int]),
             "dstr_set_overlap": (C.c_int, [vp, C.c_int]),
+            "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+            "dstr_set_pyramid_outputs": (C.c_int, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = (
     "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
-    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap"
+    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_downscale2x dstr_set_pyramid_outputs"
 ).split()
 
 
@@ -405,6 +407,24 @@ class DestripeEngine:
 
     def set_notch_tolerance(self, eps: float):
         self._ck(self.lib.dstr_set_notch_tolerance(self.ctx, float(eps)), "dstr_set_notch_tolerance")
+
+    def downscale2x(self, vol: np.ndarray) -> np.ndarray:
+        """uint16 (Z, H, W) -> (Z//2, H//2, W//2): truncated 2x2x2 windowed mean (one pyramid level)."""
+        vol = np.ascontiguousarray(vol)
+        if vol.dtype != np.uint16 or vol.ndim != 3:
+            raise ValueError("downscale2x expects a uint16 (Z, H, W) array")
+        Z, H, W = vol.shape
+        out = np.empty((Z // 2, H // 2, W // 2), dtype=np.uint16)
+        self._ck(self.lib.dstr_downscale2x(self.ctx, vol.ctypes.data_as(C.c_void_p), Z, H, W,
+                                           out.ctypes.data_as(C.c_void_p)), "dstr_downscale2x")
+        return out
+
+    def set_pyramid_outputs(self, level1: Optional[np.ndarray], level2: Optional[np.ndarray] = None):
+        """Host arrays that receive pyramid levels 1 / 2 of the next filtered uint16 chunks."""
+        p1 = level1.ctypes.data_as(C.c_void_p) if level1 is not None else None
+        p2 = level2.ctypes.data_as(C.c_void_p) if level2 is not None else None
+        self._ck(self.lib.dstr_set_pyramid_outputs(self.ctx, p1, p2), "dstr_set_pyramid_outputs")
+        self._pyr_refs = (level1, level2)
 
     def set_overlap(self, enabled: bool):
         self._ck(self.lib.dstr_set_overlap(self.ctx, 1 if enabled else 0), "dstr_set_overlap")

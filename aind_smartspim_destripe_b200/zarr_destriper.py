@@ -113,6 +113,33 @@ def execute_worker(
 
 
 # ----------------------------------------------------------------------------------------------
+def compute_pyramid(data, n_lvls: int, scale_axis, chunks="auto", engine: Optional["_eng.DestripeEngine"] = None):
+    """Multiscale levels ``[level 0, ..., level n_lvls-1]`` of a uint16 volume on the GPU.
+
+    Mirrors reference ``compute_pyramid`` (zarr_destriper.py:365-407): windowed mean with
+    ``preserve_dtype`` (truncation), every level built from the previous one; only the
+    reference's scale ``2`` on the last three axes (leading axes 1) is implemented.
+    """
+    data = np.asarray(data)
+    scale_axis = tuple(int(s) for s in scale_axis)
+    if data.dtype != np.uint16 or data.ndim < 3:
+        raise NotImplementedError("B200 engine: compute_pyramid expects a uint16 array with >= 3 dimensions")
+    if scale_axis[-3:] != (2, 2, 2) or any(s != 1 for s in scale_axis[:-3]) or len(scale_axis) != data.ndim:
+        raise NotImplementedError("B200 engine: only scale (…, 1, 2, 2, 2) is implemented")
+    lead = data.shape[:-3]
+    if int(np.prod(lead)) != 1:
+        raise NotImplementedError("B200 engine: leading (T, C) axes must be singleton")
+    levels = [data]
+    vol = data.reshape(data.shape[-3:])
+    eng = engine
+    for _ in range(1, n_lvls):
+        if eng is None:
+            eng = _eng.get_engine(vol.shape[1], vol.shape[2])
+        vol = eng.downscale2x(vol)
+        levels.append(vol.reshape(lead + vol.shape))
+    return levels
+
+
 def z_slab(n_planes: int, rank: int, world_size: int, align: int = 64) -> Tuple[int, int]:
     """Contiguous Z range ``[z0, z1)`` of ``rank``; boundaries are multiples of ``align``."""
     if world_size <= 0 or not (0 <= rank < world_size):
@@ -136,10 +163,16 @@ def destripe_volume(
     device: Optional[int] = None,
     microscope_high_int: int = 2500,
     queue_depth: int = 2,
+    pyramid_outputs: Optional[Sequence] = None,
 ):
     """Stream ``volume[z0:z1]`` (array-like ``(Z, H, W)``, uint16 or float32) through the GPU.
 
     ``output`` is any ``(Z, H, W)`` sink with ``__setitem__`` (numpy array, zarr array).
+    ``pyramid_outputs`` (optional): up to two sinks ``(Z//2, H//2, W//2)`` and ``(Z//4, H//4, W//4)``
+    that receive multiscale levels 1 and 2, computed on the device while each destriped chunk is
+    still resident (requires ``shadow_correction``, i.e. uint16 output, and ``chunk_planes`` and
+    the slab start to be multiples of 4).
+
     Returns a timing dict: ``read_s`` (decode / host I/O), ``device_s`` (pinned H2D + kernels +
     D2H inside the engine), ``write_s`` and ``wall_s``.
     """
@@ -148,7 +181,13 @@ def destripe_volume(
     eng = _eng.DestripeEngine(H, W, max_planes=min(chunk_planes, 16), device=_eng.default_device() if device is None else device)
     in_dtype = np.uint16 if np.dtype(volume.dtype) == np.uint16 else np.float32
     out_dtype = np.uint16 if shadow_correction is not None else np.float32
+    n_pyr = 0 if pyramid_outputs is None else len(pyramid_outputs)
+    if n_pyr:
+        if out_dtype != np.uint16 or chunk_planes % 4 or z0 % 4 or n_pyr > 2:
+            raise ValueError("pyramid_outputs need uint16 output, chunk_planes % 4 == 0 and an aligned slab")
     n_buf = queue_depth + 1
+    pyr_bufs = [[_eng.PinnedBuffer((max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
+                 for k in range(n_pyr)] for _ in range(n_buf)]
     in_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
     out_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
     free_in: "queue.Queue[int]" = queue.Queue()
@@ -185,6 +224,10 @@ def destripe_volume(
                 t = time.perf_counter()
                 res = out_bufs[j].array[: b - a]
                 output[a:b] = res if out_dtype == np.uint16 else np.clip(res, 0, 65535)
+                for k in range(n_pyr):
+                    sh = k + 1
+                    n_k = (b - a) >> sh
+                    pyramid_outputs[k][(a >> sh) : (a >> sh) + n_k] = pyr_bufs[j][k].array[:n_k]
                 times["write_s"] += time.perf_counter() - t
                 free_out.put(j)
         except Exception as exc:  # pragma: no cover
@@ -204,6 +247,8 @@ def destripe_volume(
             i, a, b = item
             j = free_out.get()
             t = time.perf_counter()
+            if n_pyr:
+                eng.set_pyramid_outputs(pyr_bufs[j][0].array, pyr_bufs[j][1].array if n_pyr > 1 else None)
             fl.filter_planes(
                 in_bufs[i].array[: b - a],
                 tile,
@@ -222,7 +267,7 @@ def destripe_volume(
         rt.join()
         wt.join()
         times["wall_s"] = time.perf_counter() - t_wall
-        for pb in in_bufs + out_bufs:
+        for pb in in_bufs + out_bufs + [p for ps in pyr_bufs for p in ps]:
             pb.free()
         eng.close()
     if errors:

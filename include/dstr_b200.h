@@ -108,6 +108,17 @@ int dstr_plane_stats(dstr_ctx* ctx, const void* in, int in_dtype, int Z, double*
 int dstr_flatfield_correction(int device, const float* img, const float* flat, const float* dark,
                               const float* baseline, uint16_t* out, int n_outer, int H, int W);
 
+/* ---- next row f3: multiscale pyramid ---------------------------------------------------------
+ * Replaces: compute_pyramid / xarray_multiscale.windowed_mean with preserve_dtype, scale (2,2,2)
+ * (zarr_destriper.py:365-407, :741-749): out = uint16(floor(mean of each 2x2x2 block)); odd
+ * trailing planes / rows / columns are cropped.  Host or device pointers. */
+int dstr_downscale2x(dstr_ctx* ctx, const uint16_t* in, int Z, int H, int W, uint16_t* out);
+/* Fused variant: while a destriped uint16 batch is still resident, the following
+ * dstr_filter_chunk calls also emit pyramid level 1 ((Z/2, H/2, W/2)) and, if non-NULL, level 2
+ * ((Z/4, H/4, W/4), the windowed mean of level 1, like the reference which re-reads the written
+ * level).  Z of the chunk should be a multiple of 4.  NULL level1 disables. */
+int dstr_set_pyramid_outputs(dstr_ctx* ctx, void* level1, void* level2);
+
 /* ---- geometry / tables (host only, no GPU work) ---------------------------------------------
  * Replaces: pywt.dwtn_max_level / dwt_coeff_len bookkeeping behind pywt.wavedec2
  * (filtering.py:176). */

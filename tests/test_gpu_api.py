@@ -162,3 +162,35 @@ def test_error_paths():
     with pytest.raises(ValueError):
         eng.set_flat_dark(np.ones((64, 81), np.float32), np.ones((64, 80), np.float32))
     eng.close()
+
+
+def test_downscale_and_fused_pyramid_match_oracle(production_configs):
+    # next-row f3: xarray_multiscale windowed_mean + preserve_dtype (zarr_destriper.py:365-407)
+    from oracle import pyramid as OP
+
+    no_cells, cells = production_configs
+    rng = np.random.default_rng(5)
+    vol = rng.integers(0, 65536, (9, 37, 50)).astype(np.uint16)  # odd sizes are cropped
+    eng = E.DestripeEngine(37, 50, max_planes=4)
+    np.testing.assert_array_equal(eng.downscale2x(vol), OP.windowed_mean(vol, (2, 2, 2)))
+    eng.close()
+    lv = zd.compute_pyramid(vol[None, None], 3, (1, 1, 2, 2, 2))
+    ref = OP.compute_pyramid(vol[None, None], 3, (1, 1, 2, 2, 2))
+    assert len(lv) == 3
+    for a, b in zip(lv, ref):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(NotImplementedError):
+        zd.compute_pyramid(vol[None, None], 2, (1, 1, 2, 2, 4))
+
+    # fused: pyramid levels emitted while the destriped chunk is resident == pyramid of the output
+    Z, H, W = 24, 160, 192
+    st = S.synthetic_stack(Z, H, W, base_seed=51, cells_every=3, n_unique=6)
+    shadow = _shadow(H, W)
+    out = np.zeros((Z, H, W), np.uint16)
+    p1 = np.zeros((Z // 2, H // 2, W // 2), np.uint16)
+    p2 = np.zeros((Z // 4, H // 4, W // 4), np.uint16)
+    zd.destripe_volume(st, out, no_cells, cells, shadow, chunk_planes=8, pyramid_outputs=(p1, p2))
+    ref = OP.compute_pyramid(out, 3, (2, 2, 2))
+    np.testing.assert_array_equal(p1, ref[1])
+    np.testing.assert_array_equal(p2, ref[2])
+    np.testing.assert_array_equal(out, fl.filter_planes(st, "0_0", no_cells, cells, shadow, 2500))

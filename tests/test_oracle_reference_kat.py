@@ -120,3 +120,19 @@ def test_filter_stripes_branches(production_configs):  # :242-281 (plumbing; her
     out_s = F.filter_stripes(dim, "0_0", no_cells, cells, shadow_correction=shadow)
     assert out_s.dtype == np.uint16 and out_s.shape == (64, 64)
     np.testing.assert_array_equal(out_s, np.clip((np.maximum(out_dim - 10, 0)) / 2.0, 0, 65535).astype(np.uint16))
+
+
+def test_windowed_mean_pyramid_oracle():
+    # xarray_multiscale.windowed_mean + preserve_dtype semantics (zarr_destriper.py:399-405)
+    from oracle import pyramid as OP
+
+    a = np.arange(2 * 4 * 6, dtype=np.uint16).reshape(2, 4, 6)
+    r = OP.windowed_mean(a, (2, 2, 2))
+    assert r.shape == (1, 2, 3) and r.dtype == np.uint16
+    assert r[0, 0, 0] == (0 + 1 + 6 + 7 + 24 + 25 + 30 + 31) // 8
+    b = np.array([[[1, 2], [2, 2]], [[2, 2], [2, 2]]], dtype=np.uint16)  # mean 1.875 -> truncates to 1
+    assert OP.windowed_mean(b, (2, 2, 2))[0, 0, 0] == 1
+    odd = np.ones((3, 5, 7), np.uint16)
+    assert OP.windowed_mean(odd, (2, 2, 2)).shape == (1, 2, 3)
+    lv = OP.compute_pyramid(np.ones((1, 1, 8, 8, 8), np.uint16), 3, (1, 1, 2, 2, 2))
+    assert [x.shape for x in lv] == [(1, 1, 8, 8, 8), (1, 1, 4, 4, 4), (1, 1, 2, 2, 2)]
