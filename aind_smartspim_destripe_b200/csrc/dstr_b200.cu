@@ -553,7 +553,7 @@ int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
     fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
     const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
                                          (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
-                                         (size_t)FR_ROWS * fa.Jpad_max + (size_t)FR_ROWS * FR_ROWS * fa.Jpad_max);
+                                         (size_t)3 * FR_ROWS * fa.Jpad_max);  // 64-bit accumulators + float copy
     if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
     const int epl = (g.W + 31) / 32;
     if (epl <= 2) return launch_filter<2>(ctx, fa, P.z, smem, P.dp, st);

@@ -730,8 +730,10 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     float* s_to = s_te + a.ntap_e_max;                  // [ntap_o_max]
     float* s_E = s_to + a.ntap_o_max;                   // [FR_ROWS][xlen_e_phys]
     float* s_O = s_E + FR_ROWS * a.xlen_e_phys;         // [FR_ROWS][xlen_o_phys]
-    float* s_c = s_O + FR_ROWS * a.xlen_o_phys;         // [FR_ROWS][Jpad_max]
-    float* s_part = s_c + FR_ROWS * a.Jpad_max;         // [FR_ROWS warps][FR_ROWS][Jpad_max]
+    // rank-J coefficients: accumulated as 64-bit fixed point (deterministic, order-free atomics),
+    // then converted to float
+    unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * a.xlen_o_phys);  // [FR_ROWS][Jpad_max]
+    float* s_c = reinterpret_cast<float*>(s_c64 + FR_ROWS * a.Jpad_max);                                // [FR_ROWS][Jpad_max]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int z = blockIdx.y;
@@ -745,6 +747,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
 
     for (int i = tid; i < nt.ntap_e; i += FR_THREADS) s_te[i] = nt.te[i];
     for (int i = tid; i < nt.ntap_o; i += FR_THREADS) s_to[i] = nt.to[i];
+    for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS) s_c64[i] = 0ull;
 
     float* E = s_E + wid * a.xlen_e_phys;
     float* O = s_O + wid * a.xlen_o_phys;
@@ -882,21 +885,19 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
                     acc[r][1] = fmaf(xe, t1, acc[r][1]);
                 }
             }
+            // each warp holds the partial sums of its range of v: combine in shared memory as
+            // 2^-32 fixed point (|c_j| < 2^30 by far; integer adds commute, so the result does
+            // not depend on the order in which the warps arrive)
 #pragma unroll
             for (int r = 0; r < FR_ROWS; ++r) {
-                float* pp = s_part + ((size_t)wid * FR_ROWS + r) * a.Jpad_max + j0 + lane;
-                pp[0] = acc[r][0];
-                if (two) pp[32] = acc[r][1];
+                unsigned long long* pp = s_c64 + r * a.Jpad_max + j0 + lane;
+                atomicAdd(pp, (unsigned long long)__float2ll_rn(acc[r][0] * 4294967296.0f));
+                if (two) atomicAdd(pp + 32, (unsigned long long)__float2ll_rn(acc[r][1] * 4294967296.0f));
             }
         }
         __syncthreads();
-        for (int i = tid; i < FR_ROWS * Jpad; i += FR_THREADS) {
-            const int r = i / Jpad, j = i - r * Jpad;
-            float sum = 0.f;
-#pragma unroll
-            for (int w = 0; w < FR_ROWS; ++w) sum += s_part[((size_t)w * FR_ROWS + r) * a.Jpad_max + j];
-            s_c[r * a.Jpad_max + j] = sum;
-        }
+        for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS)
+            s_c[i] = __ll2float_rn((long long)s_c64[i]) * (1.0f / 4294967296.0f);
         __syncthreads();
     }
 
