@@ -234,8 +234,14 @@ struct RawPair<IN_T, false> {
 // VEC: Hs, Ws >= 8, Ws even, even pitch / plane stride: every (reflected) column pair is an aligned
 // two-element word, possibly swapped, and one reflection per index suffices; otherwise two scalar
 // loads per row with the general (repeated) reflection.
+#ifndef DSTR_AN_MINB
+#define DSTR_AN_MINB 1
+#endif
+#ifndef DSTR_SY_MINB
+#define DSTR_SY_MINB 1
+#endif
 template <typename IN_T, bool FIRST, bool STATS, bool VEC>
-__global__ void __launch_bounds__(AN_THREADS)
+__global__ void __launch_bounds__(AN_THREADS, DSTR_AN_MINB)
 analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_t in_pstride,
                 float* __restrict__ cA, float* __restrict__ cH, int Ho, int Wo, int out_pitch,
                 size_t out_pstride, LevelStat* __restrict__ lstat, int stat_stride,
@@ -975,7 +981,7 @@ struct EpilogueArgs {
 // VEC (FINAL only): Wo and the plane stride are even, so the two pixels of a lane are one aligned
 // word of the image, of the output and of the dark / flat fields.
 template <bool FINAL, typename IN_T, typename OUT_T, bool VEC>
-__global__ void __launch_bounds__(SY_THREADS)
+__global__ void __launch_bounds__(SY_THREADS, DSTR_SY_MINB)
 synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl, int Wl, int pitch_l,
              size_t pstride_l, float* __restrict__ outA, int Ho, int Wo, int pitch_o,
              size_t pstride_o, const IN_T* __restrict__ img, OUT_T* __restrict__ out,

@@ -14,7 +14,9 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdstr_b200.so")
+_LIB_PATH = os.environ.get(
+    "DSTR_LIBRARY", os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdstr_b200.so")
+)
 
 DSTR_U16, DSTR_F32 = 0, 1
 MODE_LOGSPACE, MODE_DISPATCH = 0, 1
