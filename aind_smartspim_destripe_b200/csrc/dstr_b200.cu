@@ -66,7 +66,8 @@ struct dstr_ctx {
     int device = 0;
     int zcap = 0;
     int H = 0, W = 0;
-    int Lmax = 0;
+    int Lmax = 0;    // pywt.dwtn_max_level of the plane shape (what level=None means)
+    int Lalloc = 0;  // levels with workspace: deeper explicit levels are allowed like in pywt (it only warns)
     LevelGeom geom[kMaxLevels + 1];
     float* d_A[kMaxLevels + 1] = {};
     float* d_H[kMaxLevels + 1] = {};
@@ -652,7 +653,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
     ctx->last_z = z;
 
     ScopedTimer t_all(ctx, 7);
-    if (L > 0) CK(ctx, cudaMemsetAsync(ctx->d_lstat, 0, sizeof(LevelStat) * P.level_stride * ctx->Lmax, st));
+    if (L > 0) CK(ctx, cudaMemsetAsync(ctx->d_lstat, 0, sizeof(LevelStat) * P.level_stride * L, st));
     CK(ctx, cudaMemsetAsync(ctx->d_pstat, 0, sizeof(PlaneStat) * ctx->zcap, st));
 
     const bool staged = ctx->profiling || ctx->debug_stop != DSTR_STAGE_NONE || !ctx->overlap;
@@ -845,6 +846,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
     ctx->H = H;
     ctx->W = W;
     ctx->Lmax = std::min(std::min(max_level_1d(H), max_level_1d(W)), kMaxLevels);
+    ctx->Lalloc = std::min(kMaxLevels, ctx->Lmax + 4);
     *out = nullptr;
 #define CKC(call)                                                                         \
     do {                                                                                  \
@@ -857,7 +859,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
     } while (0)
     CKC(cudaSetDevice(device));
     ctx->geom[0] = {H, W, W, (size_t)H * W};
-    for (int l = 1; l <= ctx->Lmax; ++l) {
+    for (int l = 1; l <= ctx->Lalloc; ++l) {
         LevelGeom g;
         g.H = (ctx->geom[l - 1].H + kFilterTaps - 1) / 2;
         g.W = (ctx->geom[l - 1].W + kFilterTaps - 1) / 2;
@@ -868,7 +870,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * (g.pstride * max_planes + 8)));
         CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 8)));
     }
-    if (ctx->Lmax > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lmax * max_planes));
+    if (ctx->Lalloc > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lalloc * max_planes));
     CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));
     CKC(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     {
@@ -990,8 +992,8 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
     if (Lc != L)
         return fail(ctx, DSTR_E_UNSUPPORTED,
                     "cells/no_cells use different decomposition levels: split the chunk by config");
-    if (L > ctx->Lmax)
-        return fail(ctx, DSTR_E_UNSUPPORTED, "level exceeds pywt.dwtn_max_level for this plane shape");
+    if (L > ctx->Lalloc)
+        return fail(ctx, DSTR_E_UNSUPPORTED, "level exceeds pywt.dwtn_max_level for this plane shape by more than 4");
     CK(ctx, cudaSetDevice(ctx->device));
 
     for (int l = 1; l <= L; ++l) {
@@ -1370,7 +1372,7 @@ int dstr_set_subchunk(dstr_ctx* ctx, int planes) {
 
 int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_t host_bytes) {
     if (!ctx || !host_buf) return DSTR_E_ARG;
-    if (level < 1 || level > ctx->Lmax) return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: bad level");
+    if (level < 1 || level > ctx->Lalloc) return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: bad level");
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     const int Z = ctx->last_z;

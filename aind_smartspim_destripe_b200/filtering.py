@@ -133,6 +133,12 @@ def log_space_fft_filtering(
         planes = planes[None]
     Z, H, W = planes.shape
     eng = _eng.get_engine(H, W, max_planes=max(16, Z) if stack else 16)
+    if level is not None and level > eng.max_level:
+        import warnings
+
+        warnings.warn(  # same condition and text as pywt's wavedec2 (_multilevel._check_level)
+            f"Level value of {level} is too high: all coefficients will experience boundary effects."
+        )
     flags = _eng.FLAG_STACK_OTSU if stack and Z > 1 else 0
     out = eng.filter_chunk(planes, params, out_dtype=np.float32, mode=_eng.MODE_LOGSPACE, flags=flags)
     out = out.astype(np.float64)

@@ -142,8 +142,11 @@ def test_level_zero_and_explicit_levels():
         ref = OF.log_space_fft_filtering(img, level=lvl, sigma=64, max_threshold=4)
         out = fl.log_space_fft_filtering(img, level=lvl, sigma=64, max_threshold=4)
         assert rel_err(out, ref) < REL_TOL
+    with pytest.warns(UserWarning):  # > dwtn_max_level: pywt warns and proceeds, so does the engine
+        out6 = fl.log_space_fft_filtering(img, level=6, sigma=64, max_threshold=4)
+    assert rel_err(out6, OF.log_space_fft_filtering(img, level=6, sigma=64, max_threshold=4)) < REL_TOL
     with pytest.raises(NotImplementedError):
-        fl.log_space_fft_filtering(img, level=9)  # > dwtn_max_level: pywt only warns; engine refuses
+        fl.log_space_fft_filtering(img, level=12)  # more than 4 levels past the maximum: refused
     with pytest.raises(NotImplementedError):
         fl.log_space_fft_filtering(img, wavelet="haar", level=1)
 
