@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--unique-planes", type=int, default=16)
     ap.add_argument("--subchunk", type=int, default=0, help="planes per H2D/compute/D2H pipeline stage in the e2e leg (0 = engine default)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU-baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--no-overlap", action="store_true", help="issue every kernel on one stream in stage order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -187,7 +188,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -200,6 +201,7 @@ def run_b200(args):
     rank, world, local = D.init()
     device = local if world > 1 else int(os.environ.get("DSTR_DEVICE", "0"))
     torch.cuda.set_device(device)
+    numa = None if args.no_numa_bind else D.bind_to_gpu_numa(device)
     Z, H, W = args.planes, args.height, args.width
     px_per_step = Z * H * W
 
@@ -313,11 +315,12 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "planes_per_launch": batch,
                        "l2_policy": "inputs (1.07 GB/chunk) larger than L2; no flush needed",
-                       "sharding": f"one chunk per rank, {world} rank(s), no collective"},
+                       "sharding": f"one chunk per rank, {world} rank(s), no collective",
+                       "numa_node_rank0": numa},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     d_in.free()
     d_out.free()
     eng.close()
@@ -326,10 +329,25 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # Exactly one JSON line may reach stdout: libraries (e.g. the NCCL version banner) write to
+    # file descriptor 1 behind Python's back, so everything but the final line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 if __name__ == "__main__":
