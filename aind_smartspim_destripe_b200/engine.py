@@ -451,8 +451,9 @@ class DestripeEngine:
         return out
 
 
-_engines = {}
+_engines = {}  # insertion-ordered: least recently used first
 _engines_lock = threading.Lock()
+_MAX_CACHED_ENGINES = 6  # each engine owns a device workspace proportional to max_planes * H * W
 
 
 def default_device() -> int:
@@ -461,17 +462,26 @@ def default_device() -> int:
 
 
 def get_engine(H: int, W: int, device: Optional[int] = None, max_planes: int = 16) -> DestripeEngine:
-    """Per-thread cached engine for a plane shape (the functional API uses this)."""
+    """Per-thread cached engine for a plane shape (the functional API uses this).
+
+    The cache is a small LRU: the reference API is stateless, so callers that sweep many plane
+    shapes must not accumulate one device workspace per shape.
+    """
     if device is None:
         device = default_device()
     key = (threading.get_ident(), int(device), int(H), int(W))
     with _engines_lock:
-        eng = _engines.get(key)
-        if eng is None or eng.max_planes < max_planes:
-            if eng is not None:
-                eng.close()
+        eng = _engines.pop(key, None)
+        if eng is not None and eng.max_planes < max_planes:
+            eng.close()
+            eng = None
+        if eng is None:
+            while len(_engines) >= _MAX_CACHED_ENGINES:
+                _, old = next(iter(_engines.items()))
+                _engines.pop(next(iter(_engines)))
+                old.close()
             eng = DestripeEngine(H, W, max_planes=max_planes, device=device)
-            _engines[key] = eng
+        _engines[key] = eng  # most recently used last
         return eng
 
 
