@@ -451,9 +451,10 @@ class DestripeEngine:
         return out
 
 
-_engines = {}  # insertion-ordered: least recently used first
+_tls = threading.local()  # per-thread engine cache (an engine is not thread-safe)
+_all_caches = []          # for release_engines()
 _engines_lock = threading.Lock()
-_MAX_CACHED_ENGINES = 6  # each engine owns a device workspace proportional to max_planes * H * W
+_MAX_CACHED_ENGINES = 6   # each engine owns a device workspace proportional to max_planes * H * W
 
 
 def default_device() -> int:
@@ -464,29 +465,34 @@ def default_device() -> int:
 def get_engine(H: int, W: int, device: Optional[int] = None, max_planes: int = 16) -> DestripeEngine:
     """Per-thread cached engine for a plane shape (the functional API uses this).
 
-    The cache is a small LRU: the reference API is stateless, so callers that sweep many plane
-    shapes must not accumulate one device workspace per shape.
+    The cache is a small per-thread LRU: the reference API is stateless, so callers that sweep
+    many plane shapes must not accumulate one device workspace per shape, and an eviction can only
+    close an engine of the calling thread (which is not inside a call at that moment).
     """
     if device is None:
         device = default_device()
-    key = (threading.get_ident(), int(device), int(H), int(W))
-    with _engines_lock:
-        eng = _engines.pop(key, None)
-        if eng is not None and eng.max_planes < max_planes:
-            eng.close()
-            eng = None
-        if eng is None:
-            while len(_engines) >= _MAX_CACHED_ENGINES:
-                _, old = next(iter(_engines.items()))
-                _engines.pop(next(iter(_engines)))
-                old.close()
-            eng = DestripeEngine(H, W, max_planes=max_planes, device=device)
-        _engines[key] = eng  # most recently used last
-        return eng
+    cache = getattr(_tls, "engines", None)
+    if cache is None:
+        cache = _tls.engines = {}
+        with _engines_lock:
+            _all_caches.append(cache)
+    key = (int(device), int(H), int(W))
+    eng = cache.pop(key, None)
+    if eng is not None and eng.max_planes < max_planes:
+        eng.close()
+        eng = None
+    if eng is None:
+        while len(cache) >= _MAX_CACHED_ENGINES:
+            cache.pop(next(iter(cache))).close()  # least recently used
+        eng = DestripeEngine(H, W, max_planes=max_planes, device=device)
+    cache[key] = eng  # most recently used last
+    return eng
 
 
 def release_engines():
+    """Close every cached engine (call only when no thread is inside the functional API)."""
     with _engines_lock:
-        for eng in _engines.values():
-            eng.close()
-        _engines.clear()
+        for cache in _all_caches:
+            for eng in list(cache.values()):
+                eng.close()
+            cache.clear()
