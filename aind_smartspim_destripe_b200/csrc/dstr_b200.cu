@@ -675,7 +675,11 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
             if (ctx->debug_stop == DSTR_STAGE_OTSU) return 0;
             {
                 ScopedTimer t(ctx, 4);
-                for (int l = 1; l <= L; ++l) RC(launch_filter_level(P, l, st));
+                {
+                    ScopedTimer t1(ctx, 8);
+                    RC(launch_filter_level(P, 1, st));
+                }
+                for (int l = 2; l <= L; ++l) RC(launch_filter_level(P, l, st));
             }
             if (ctx->debug_stop == DSTR_STAGE_FILTER) return 0;
             {

@@ -24,7 +24,7 @@ FLAG_SHADOW, FLAG_EXPM1, FLAG_STACK_OTSU, FLAG_NO_SYNC = 1, 2, 4, 8
 STAGE_NONE, STAGE_ANALYSIS, STAGE_OTSU, STAGE_FILTER, STAGE_SYNTH = 0, 1, 2, 3, 4
 FETCH_CA, FETCH_CH, FETCH_STATS, FETCH_HIST = 0, 1, 2, 3
 E_ARG, E_SHAPE, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4
-NUM_TIMERS = 8
+NUM_TIMERS = 9
 TIMER_NAMES = (
     "analysis_l1",
     "analysis_deep",
@@ -34,6 +34,7 @@ TIMER_NAMES = (
     "synthesis_deep",
     "final_synthesis_epilogue",
     "chunk_total",
+    "row_filter_level1",
 )
 
 

@@ -158,9 +158,11 @@ int dstr_synchronize(dstr_ctx* ctx);
 void* dstr_compute_stream(dstr_ctx* ctx);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
-#define DSTR_NUM_TIMERS 8
-/* timers: 0 analysis L1, 1 analysis L2+, 2 histogram, 3 otsu, 4 row filter, 5 synthesis L2+,
- *         6 final synthesis+epilogue, 7 whole chunk (device time, ms, accumulated). */
+#define DSTR_NUM_TIMERS 9
+/* timers: 0 analysis L1, 1 analysis L2+, 2 histogram, 3 otsu, 4 row filter (all levels), 5 synthesis
+ *         L2+, 6 final synthesis+epilogue, 7 whole chunk, 8 row filter level 1 alone (the single
+ *         dominant kernel launch).  Device time in ms, accumulated; profiling mode issues the pass
+ *         stage by stage on one stream. */
 int dstr_set_profiling(dstr_ctx* ctx, int enabled);
 int dstr_get_timers(dstr_ctx* ctx, double* ms_out /*[DSTR_NUM_TIMERS]*/, uint64_t* launches_out);
 int dstr_reset_timers(dstr_ctx* ctx);
