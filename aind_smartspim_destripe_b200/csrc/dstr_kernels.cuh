@@ -187,7 +187,10 @@ __device__ __forceinline__ float fast_exp(float x) {
 // so lanes 2..31 emit outputs ox0 .. ox0+29.  Halo cost: 4 extra input rows per 2*AN_TOY and
 // 2 of 32 lanes.  The row loop is unrolled by 3 (the period of the 6-row window).
 // =============================================================================================
-constexpr int AN_TOY = 24;
+#ifndef DSTR_AN_TOY
+#define DSTR_AN_TOY 24
+#endif
+constexpr int AN_TOY = DSTR_AN_TOY;  // multiple of 3
 constexpr int AN_OXW = 30;  // output columns per warp
 constexpr int AN_WX = 2;    // warps of a block along x ...
 constexpr int AN_WY = 4;    // ... and along y
@@ -967,8 +970,14 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
 // loop unrolled by 3).
 // =============================================================================================
 constexpr int SY_TX = 64;
-constexpr int SY_TY = 48;
-constexpr int SY_WARPS = 8;
+#ifndef DSTR_SY_TY
+#define DSTR_SY_TY 48
+#endif
+constexpr int SY_TY = DSTR_SY_TY;  // multiple of 6
+#ifndef DSTR_SY_WARPS
+#define DSTR_SY_WARPS 4
+#endif
+constexpr int SY_WARPS = DSTR_SY_WARPS;
 constexpr int SY_THREADS = 32 * SY_WARPS;
 
 struct EpilogueArgs {
