@@ -90,6 +90,7 @@ struct dstr_ctx {
     cudaStream_t s_side[4] = {};                       // per-level hist/otsu/filter branches
     cudaEvent_t ev_an[kMaxLevels + 1] = {}, ev_flt[kMaxLevels + 1] = {};
     bool overlap = true;
+    bool use_tma = true;  // level-1 analysis through the TMA-staged kernel when the plane shape allows
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     float fg_half_thr = 384.f;
     double notch_eps = 1e-6;  // truncation tolerance of the hybrid notch operator (0 = dense)
@@ -444,7 +445,19 @@ void resolve_timers(dstr_ctx* ctx) {
 template <int EPL>
 int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem, const DispatchParams& dp,
                   cudaStream_t st) {
-    CK(ctx, cudaFuncSetAttribute(filter_rows_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // opt in to the full dynamic shared memory once per instantiation and device (never lowered, so
+    // concurrent contexts in other host threads cannot invalidate each other's launches)
+    static std::mutex mtx;
+    static bool done[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        const int dev = ctx->device & 63;
+        if (!done[dev]) {
+            CK(ctx, cudaFuncSetAttribute(filter_rows_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
+            done[dev] = true;
+        }
+    }
     dim3 grid((fa.Hl + FR_ROWS - 1) / FR_ROWS, Z);
     filter_rows_kernel<EPL><<<grid, FR_THREADS, smem, st>>>(fa, ctx->d_pstat, dp);
     ctx->launches++;
@@ -482,7 +495,24 @@ int launch_analysis(const Pass& P, int l, cudaStream_t st) {
     } while (0)
     // aligned two-element loads need an even width, pitch and plane stride
     const bool vec = (gs.W % 2 == 0) && (gs.W >= 8) && (gs.H >= 8) && (gs.pitch % 2 == 0) && (gs.pstride % 2 == 0);
-    if (l == 1) {
+    const size_t esz = P.in_dtype == DSTR_U16 ? 2 : 4;
+    if (l == 1 && ctx->use_tma && W >= AT_WIN && (W * esz) % 16 == 0 && ((size_t)H * W * esz) % 16 == 0 && H >= 8 &&
+        ((uintptr_t)P.d_in % 16) == 0) {
+        const int rows_per_cta = 126;  // multiple of 3; 2.4 % halo rows
+        dim3 gt((go.W + AT_OXB - 1) / AT_OXB, (go.H + rows_per_cta - 1) / rows_per_cta, z);
+#define LAUNCH_TMA(IN_T, ST)                                                                              \
+    analysis_tma_kernel<IN_T, ST><<<gt, AT_THREADS, 0, st>>>((const IN_T*)P.d_in, H, W, (size_t)H * W, ctx->d_A[1], \
+                                                              ctx->d_H[1], go.H, go.W, go.pitch, go.pstride, ls,  \
+                                                              P.stat_stride, ctx->d_pstat, ctx->fg_half_thr, rows_per_cta)
+        if (P.in_dtype == DSTR_U16) {
+            if (stats) LAUNCH_TMA(uint16_t, true);
+            else LAUNCH_TMA(uint16_t, false);
+        } else {
+            if (stats) LAUNCH_TMA(float, true);
+            else LAUNCH_TMA(float, false);
+        }
+#undef LAUNCH_TMA
+    } else if (l == 1) {
         if (P.in_dtype == DSTR_U16) {
             if (stats) LAUNCH_AN1V(uint16_t, true);
             else LAUNCH_AN1V(uint16_t, false);
@@ -1360,6 +1390,12 @@ int dstr_downscale2x(dstr_ctx* ctx, const uint16_t* in, int Z, int H, int W, uin
     if (!in_dev && d_in) cudaFree(d_in);
     if (!out_dev && d_out) cudaFree(d_out);
     return rc;
+}
+
+int dstr_set_tma(dstr_ctx* ctx, int enabled) {
+    if (!ctx) return DSTR_E_ARG;
+    ctx->use_tma = enabled != 0;
+    return 0;
 }
 
 int dstr_set_overlap(dstr_ctx* ctx, int enabled) {

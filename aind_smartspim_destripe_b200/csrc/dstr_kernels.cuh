@@ -13,6 +13,7 @@
 // Reference semantics restated: /root/reference/code/aind_smartspim_destripe/filtering.py:139-224
 // (log_space_fft_filtering), :54-88 (fg/bg means), :338-414 (flatfield_correction).
 #pragma once
+#include <cuda/ptx>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -413,6 +414,212 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
             double fs = 0.0, as = 0.0;
             unsigned long long fc = 0, ac = 0;
             for (int w = 0; w < AN_WARPS; ++w) {
+                fs += s_dred[0][w];
+                as += s_dred[1][w];
+                fc += s_cred[0][w];
+                ac += s_cred[1][w];
+            }
+            PlaneStat* ps = pstat + z;
+            if (fc) {
+                atomicAdd(&ps->fg_sum, fs);
+                atomicAdd(&ps->fg_cnt, fc);
+            }
+            if (ac - fc) {
+                atomicAdd(&ps->bg_sum, as - fs);
+                atomicAdd(&ps->bg_cnt, ac - fc);
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Level-1 analysis with TMA staging.  Same arithmetic and lane layout as analysis_kernel, but the
+// input rows are brought into a shared-memory ring by 1-D bulk copies (cp.async.bulk, completion
+// on an mbarrier) issued by one thread, AT_STAGES-1 stages ahead of the consumers, so every CTA
+// keeps ~15 KB of reads in flight without holding them in registers.  One CTA = 4 warps side by
+// side = 120 output columns; it walks `rows_per_cta` output rows, 3 per stage (6 input rows, the
+// period of the 6-row window).  Each staged row is an aligned window of AT_WIN input columns that
+// contains every (reflected) column the CTA needs; rows are reflected when the copy is issued.
+// Requirements (checked on the host): Ws >= AT_WIN, Ws * sizeof(IN_T) % 16 == 0.
+// =============================================================================================
+constexpr int AT_WARPS = 4;
+constexpr int AT_THREADS = 32 * AT_WARPS;
+constexpr int AT_OXB = AN_OXW * AT_WARPS;  // 120 output columns per CTA
+constexpr int AT_WIN = 256;                // staged input columns per row
+constexpr int AT_RS = 6;                   // input rows per stage
+constexpr int AT_STAGES = 6;
+
+template <typename IN_T, bool STATS>
+__global__ void __launch_bounds__(AT_THREADS)
+analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstride, float* __restrict__ cA,
+                    float* __restrict__ cH, int Ho, int Wo, int out_pitch, size_t out_pstride,
+                    LevelStat* __restrict__ lstat, int stat_stride, PlaneStat* __restrict__ pstat,
+                    float fg_half_thr, int rows_per_cta) {
+    __shared__ __align__(128) IN_T s_ring[AT_STAGES][AT_RS][AT_WIN];
+    __shared__ __align__(8) uint64_t s_full[AT_STAGES];
+    __shared__ float s_red[2][AT_WARPS];
+    __shared__ double s_dred[2][AT_WARPS];
+    __shared__ unsigned s_cred[2][AT_WARPS];
+
+    namespace ptx = cuda::ptx;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int z = blockIdx.z;
+    const int ox0b = blockIdx.x * AT_OXB;
+    const int oy0 = blockIdx.y * rows_per_cta;
+    const int R = min(rows_per_cta, Ho - oy0);       // output rows of this CTA (>= 1)
+    const int n_in = 2 * R + 4;                      // input rows it consumes
+    const int n_stages = (n_in + AT_RS - 1) / AT_RS;
+    const IN_T* src = in + (size_t)z * in_pstride;
+
+    // aligned window of staged columns: contains the reflected image of [2 ox0b - 4, 2 ox0b + 243]
+    constexpr int ALIGN_EL = 16 / (int)sizeof(IN_T);
+    int ws = 2 * ox0b - 8;
+    ws = max(0, min(ws, Ws - AT_WIN));
+    ws &= ~(ALIGN_EL - 1);
+
+    const int ox0 = ox0b + wid * AN_OXW;
+    const int p = ox0 - 2 + lane;  // column pair (2p, 2p+1)
+    const int gx0 = 2 * p, gx1 = 2 * p + 1;
+    // staged-row offsets of the two (reflected, clamped) columns of this lane
+    const int i0 = max(0, min(reflect_fast(gx0, Ws) - ws, AT_WIN - 1));
+    const int i1 = max(0, min(reflect_fast(gx1, Ws) - ws, AT_WIN - 1));
+    const bool own0 = (lane >= 2) && (gx0 < Ws) && (ox0 < Wo);
+    const bool own1 = (lane >= 2) && (gx1 < Ws) && (ox0 < Wo);
+
+    auto issue_stage = [&](int s) {  // one thread: 6 bulk row copies completing on s_full[slot]
+        const int slot = s % AT_STAGES;
+        constexpr unsigned ROW_BYTES = AT_WIN * sizeof(IN_T);
+        ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, &s_full[slot],
+                                       AT_RS * ROW_BYTES);
+#pragma unroll
+        for (int rr = 0; rr < AT_RS; ++rr) {
+            const int gy = reflect_fast(2 * oy0 - 4 + s * AT_RS + rr, Hs);
+            ptx::cp_async_bulk(ptx::space_shared, ptx::space_global, &s_ring[slot][rr][0],
+                               src + (size_t)gy * Ws + ws, ROW_BYTES, &s_full[slot]);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < AT_STAGES; ++i) ptx::mbarrier_init(&s_full[i], 1);
+        ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < AT_STAGES - 1 && s < n_stages; ++s) issue_stage(s);
+    }
+
+    float fg_s = 0.f, all_s = 0.f;
+    unsigned fg_c = 0, all_c = 0;
+    float qmin = __int_as_float(0x7f800000), qmax = 0.f;
+    float w0[6], w1[6];
+    const int gox = ox0 + lane - 2;
+    const bool col_ok = (lane >= 2) && (gox < Wo) && (ox0 < Wo);
+    float* oA = cA + (size_t)z * out_pstride + (size_t)oy0 * out_pitch + gox;
+    float* oH = cH + (size_t)z * out_pstride + (size_t)oy0 * out_pitch + gox;
+
+    for (int s = 0; s < n_stages; ++s) {
+        __syncthreads();  // every warp is done with stage s-1: its slot may be refilled
+        if (tid == 0 && s + AT_STAGES - 1 < n_stages) issue_stage(s + AT_STAGES - 1);
+        const int slot = s % AT_STAGES;
+        const unsigned parity = (unsigned)(s / AT_STAGES) & 1u;
+        while (!ptx::mbarrier_try_wait_parity(&s_full[slot], parity)) {
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // local input rows r = 6s + 2k, 6s + 2k + 1 enter the window (slot r % 6 == 2k, 2k + 1)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = s * AT_RS + 2 * k + h;
+                float v0 = to_f32(s_ring[slot][2 * k + h][i0]);
+                float v1 = to_f32(s_ring[slot][2 * k + h][i1]);
+                if (STATS) {
+                    const int gy0 = 2 * oy0 - 4 + r;
+                    if (r >= 4 && r < 4 + 2 * R && gy0 < Hs) {  // rows owned by this CTA
+                        const bool f0 = own0 && (__half2float(__float2half_rn(v0)) >= fg_half_thr);
+                        const bool f1 = own1 && (__half2float(__float2half_rn(v1)) >= fg_half_thr);
+                        all_s += own0 ? v0 : 0.f;
+                        all_s += own1 ? v1 : 0.f;
+                        all_c += (own0 ? 1u : 0u) + (own1 ? 1u : 0u);
+                        fg_s += f0 ? v0 : 0.f;
+                        fg_s += f1 ? v1 : 0.f;
+                        fg_c += (f0 ? 1u : 0u) + (f1 ? 1u : 0u);
+                    }
+                }
+                w0[2 * k + h] = DSTR_LOGF(__fadd_rn(1.0f, v0));  // np.log(1.0 + x) in float32
+                w1[2 * k + h] = DSTR_LOGF(__fadd_rn(1.0f, v1));
+            }
+            // output row oy = 3s + k - 2 uses local input rows 2oy .. 2oy+5 = the window after this pair
+            const int oy = 3 * s + k - 2;
+            float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                // tap j multiplies local row 2oy + 5 - j = 6s + 2k + 1 - j  -> slot (2k + 1 - j) mod 6
+                const float v0 = w0[(2 * k + 1 - j + 12) % 6], v1 = w1[(2 * k + 1 - j + 12) % 6];
+                a0 = fmaf(dec_lo(j), v0, a0);
+                a1 = fmaf(dec_lo(j), v1, a1);
+                d0 = fmaf(dec_hi(j), v0, d0);
+                d1 = fmaf(dec_hi(j), v1, d1);
+            }
+            const float a0m1 = __shfl_up_sync(0xffffffffu, a0, 1), a1m1 = __shfl_up_sync(0xffffffffu, a1, 1);
+            const float a0m2 = __shfl_up_sync(0xffffffffu, a0, 2), a1m2 = __shfl_up_sync(0xffffffffu, a1, 2);
+            const float d0m1 = __shfl_up_sync(0xffffffffu, d0, 1), d1m1 = __shfl_up_sync(0xffffffffu, d1, 1);
+            const float d0m2 = __shfl_up_sync(0xffffffffu, d0, 2), d1m2 = __shfl_up_sync(0xffffffffu, d1, 2);
+            float ca = dec_lo(0) * a1, ch = dec_lo(0) * d1;
+            ca = fmaf(dec_lo(1), a0, ca);
+            ca = fmaf(dec_lo(2), a1m1, ca);
+            ca = fmaf(dec_lo(3), a0m1, ca);
+            ca = fmaf(dec_lo(4), a1m2, ca);
+            ca = fmaf(dec_lo(5), a0m2, ca);
+            ch = fmaf(dec_lo(1), d0, ch);
+            ch = fmaf(dec_lo(2), d1m1, ch);
+            ch = fmaf(dec_lo(3), d0m1, ch);
+            ch = fmaf(dec_lo(4), d1m2, ch);
+            ch = fmaf(dec_lo(5), d0m2, ch);
+            if (col_ok && oy >= 0 && oy < R) {
+                oA[(size_t)oy * out_pitch] = ca;
+                oH[(size_t)oy * out_pitch] = ch;
+                const float q = __fmul_rn(ch, ch);
+                qmin = fminf(qmin, q);
+                qmax = fmaxf(qmax, q);
+            }
+        }
+    }
+
+    // block reductions -> one set of atomics per block
+    qmin = warp_min(qmin);
+    qmax = warp_max(qmax);
+    if (lane == 0) {
+        s_red[0][wid] = qmin;
+        s_red[1][wid] = qmax;
+    }
+    if (STATS) {
+        const double fs = warp_sum((double)fg_s), as = warp_sum((double)all_s);
+        fg_c = __reduce_add_sync(0xffffffffu, fg_c);
+        all_c = __reduce_add_sync(0xffffffffu, all_c);
+        if (lane == 0) {
+            s_dred[0][wid] = fs;
+            s_dred[1][wid] = as;
+            s_cred[0][wid] = fg_c;
+            s_cred[1][wid] = all_c;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float mn = s_red[0][0], mx = s_red[1][0];
+        for (int w = 1; w < AT_WARPS; ++w) {
+            mn = fminf(mn, s_red[0][w]);
+            mx = fmaxf(mx, s_red[1][w]);
+        }
+        LevelStat* st = lstat + (size_t)z * stat_stride;
+        if (mn <= mx) {
+            atomicMax(&st->qmin_inv, ~__float_as_uint(mn));
+            atomicMax(&st->qmax_bits, __float_as_uint(mx));
+        }
+        if (STATS) {
+            double fs = 0.0, as = 0.0;
+            unsigned long long fc = 0, ac = 0;
+            for (int w = 0; w < AT_WARPS; ++w) {
                 fs += s_dred[0][w];
                 as += s_dred[1][w];
                 fc += s_cred[0][w];

@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
             "dstr_debug_fetch": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_uint64]),
             "dstr_set_subchunk": (C.c_int, [vp, C.c_int]),
             "dstr_set_overlap": (C.c_int, [vp, C.c_int]),
+            "dstr_set_tma": (C.c_int, [vp, C.c_int]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
             "dstr_set_pyramid_outputs": (C.c_int, [vp, vp, vp]),
         }
@@ -122,7 +123,7 @@ EXPORTED_SYMBOLS = (
     "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
-    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_downscale2x dstr_set_pyramid_outputs"
+    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_downscale2x dstr_set_pyramid_outputs"
 ).split()
 
 
@@ -428,6 +429,9 @@ class DestripeEngine:
         p2 = level2.ctypes.data_as(C.c_void_p) if level2 is not None else None
         self._ck(self.lib.dstr_set_pyramid_outputs(self.ctx, p1, p2), "dstr_set_pyramid_outputs")
         self._pyr_refs = (level1, level2)
+
+    def set_tma(self, enabled: bool):
+        self._ck(self.lib.dstr_set_tma(self.ctx, 1 if enabled else 0), "dstr_set_tma")
 
     def set_overlap(self, enabled: bool):
         self._ck(self.lib.dstr_set_overlap(self.ctx, 1 if enabled else 0), "dstr_set_overlap")

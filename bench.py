@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--subchunk", type=int, default=0, help="planes per H2D/compute/D2H pipeline stage in the e2e leg (0 = engine default)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU-baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
+    ap.add_argument("--no-tma", action="store_true", help="level-1 analysis with the register-streaming kernel instead of the TMA ring")
     ap.add_argument("--no-overlap", action="store_true", help="issue every kernel on one stream in stage order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -212,6 +213,8 @@ def run_b200(args):
     eng = E.DestripeEngine(H, W, max_planes=batch, device=device)
     if args.no_overlap:
         eng.set_overlap(False)
+    if args.no_tma:
+        eng.set_tma(False)
     pn, pc = E.make_params(NO_CELLS), None
     mode, flags = E.MODE_LOGSPACE, 0
     if args.workload == "c3":

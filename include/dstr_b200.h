@@ -171,6 +171,9 @@ int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_
 /* 1 (default): the per-level histogram / Otsu / row-filter branches run on side streams next to
  * the analysis and synthesis chains; 0: every kernel on the compute stream in stage order */
 int dstr_set_overlap(dstr_ctx* ctx, int enabled);
+/* 1 (default): level-1 analysis through the TMA-staged kernel (cp.async.bulk ring + mbarrier) when
+ * W >= 256 and rows are 16-byte multiples; 0: always the register-streaming kernel */
+int dstr_set_tma(dstr_ctx* ctx, int enabled);
 /* sub-chunk size (planes) used when streaming host buffers; 0 restores the default */
 int dstr_set_subchunk(dstr_ctx* ctx, int planes);
 
