@@ -729,15 +729,20 @@ __device__ __forceinline__ int hist_bin(float v, float first, float inv_width, c
 }
 
 // Warp-level accumulation tuned for the extremely skewed distribution of cH^2 (most samples in
-// the first bins): the bin of the first active lane is counted for all its peers with one
-// ballot, the remaining lanes use shared-memory atomics.
-__device__ __forceinline__ void hist_add(unsigned* s_hist, int idx, int lane) {
-    const unsigned act = __ballot_sync(0xffffffffu, idx >= 0);
+// the first bins): the four bins of every lane are first compared with one reference bin (that of
+// the first active lane); the matches of the whole warp are counted with a single warp reduction
+// and one shared-memory atomic, only the rest use individual atomics.
+__device__ __forceinline__ void hist_add4(unsigned* s_hist, int i0, int i1, int i2, int i3, int lane) {
+    const unsigned act = __ballot_sync(0xffffffffu, i0 >= 0);  // i0 < 0 <=> the whole quad is out of range
     if (act == 0) return;
-    const int b0 = __shfl_sync(0xffffffffu, idx, __ffs(act) - 1);
-    const unsigned same = __ballot_sync(0xffffffffu, idx == b0);
-    if (lane == __ffs(act) - 1) atomicAdd(&s_hist[b0], __popc(same));
-    if (idx >= 0 && idx != b0) atomicAdd(&s_hist[idx], 1u);
+    const int b0 = __shfl_sync(0xffffffffu, i0, __ffs(act) - 1);
+    const int same = (i0 == b0) + (i1 == b0) + (i2 == b0) + (i3 == b0);
+    const int total = __reduce_add_sync(0xffffffffu, same);
+    if (lane == 0) atomicAdd(&s_hist[b0], (unsigned)total);
+    if (i0 >= 0 && i0 != b0) atomicAdd(&s_hist[i0], 1u);
+    if (i1 >= 0 && i1 != b0) atomicAdd(&s_hist[i1], 1u);
+    if (i2 >= 0 && i2 != b0) atomicAdd(&s_hist[i2], 1u);
+    if (i3 >= 0 && i3 != b0) atomicAdd(&s_hist[i3], 1u);
 }
 
 __global__ void __launch_bounds__(256)
@@ -775,10 +780,7 @@ hist_kernel(const float* __restrict__ cH, int Hl, int Wl, int pitch, size_t pstr
             if (c + 2 < Wl) i2 = hist_bin(v.z, first, inv_width, s_edges);
             if (c + 3 < Wl) i3 = hist_bin(v.w, first, inv_width, s_edges);
         }
-        hist_add(s_hist, i0, lane);
-        hist_add(s_hist, i1, lane);
-        hist_add(s_hist, i2, lane);
-        hist_add(s_hist, i3, lane);
+        hist_add4(s_hist, i0, i1, i2, i3, lane);
     }
     __syncthreads();
     const unsigned h = s_hist[tid];
