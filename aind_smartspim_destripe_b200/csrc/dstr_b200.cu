@@ -342,7 +342,7 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
     const int J = best_J;
     out.J = J;
     out.Jpad = (J + 31) & ~31;
-    out.T1.assign((size_t)nhp4 * out.Jpad, 0.f);
+    out.T1.assign((size_t)(nhp4 + 16) * out.Jpad, 0.f);  // 8 zero rows of margin before v = 0 and after v = nh
     out.T2.assign((size_t)std::max(J, 1) * nhp8, 0.f);
     for (int j = 0; j < J; ++j) {
         const double r = a[j] - best_G[j];
@@ -350,7 +350,7 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
         for (int v = 0; v <= nh; ++v) {
             const double omega = (v == 0 || (n % 2 == 0 && v == nh)) ? 1.0 : 2.0;
             const double c = ct[(int)(((long long)j * v) % n)];
-            out.T1[(size_t)v * out.Jpad + j] = (float)(omega * c);
+            out.T1[(size_t)(v + 8) * out.Jpad + j] = (float)(omega * c);
             out.T2[(size_t)j * nhp8 + v] = (float)(rho * c);
         }
     }
@@ -383,7 +383,7 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     D.nt.te = D.d_buf + o_te;
     D.nt.to = D.d_buf + o_to;
-    D.nt.T1 = D.d_buf + o_T1;
+    D.nt.T1 = D.d_buf + o_T1 + (hst.J > 0 ? (size_t)8 * hst.Jpad : 0);  // points at the row of v = 0
     D.nt.T2 = D.d_buf + o_T2;
     D.nt.ntap_e = hst.ntap_e;
     D.nt.ue_lo = hst.ue_lo;
@@ -1343,7 +1343,7 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
     }
     std::vector<double> c(std::max(h.J, 1), 0.0);
     for (int j = 0; j < h.J; ++j)
-        for (int v = 0; v <= nh; ++v) c[j] += (double)h.T1[(size_t)v * h.Jpad + j] * xe[v];
+        for (int v = 0; v <= nh; ++v) c[j] += (double)h.T1[(size_t)(v + 8) * h.Jpad + j] * xe[v];
     for (int t = 0; t <= nh; ++t) {
         double ye = 0.0, yo = 0.0;
         for (int k = 0; k < h.ntap_e; ++k) ye += (double)h.te[k] * xe[(((t - (h.ue_lo + k)) % n) + n) % n];

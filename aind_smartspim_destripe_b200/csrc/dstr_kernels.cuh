@@ -1077,31 +1077,38 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     __syncthreads();  // every row's E / O is complete
 
     // ---- rank-J correction coefficients  c_j = sum_v T1[v][j] x_e[v], all rows at once ----------
+    // x_e[v] sits at logical index v + OFFe of the padded E rows.  The index range is walked in the
+    // 8-element blocks of the padded layout (immediate offsets inside a block); warp w takes the
+    // w-th quarter of the blocks for all rows.  T1 carries 8 zero rows before v = 0 and after
+    // v = nh, so the partial first / last blocks need no predicates.
     if (nt.J > 0) {
         const int OFFe = nt.ue_lo + nt.ntap_e;
         const int Jpad = nt.Jpad;
         const int nv = nh + 1;
-        const int q = (nv + FR_ROWS - 1) / FR_ROWS;  // v range of this warp
-        const int v_begin = wid * q, v_end = min(nv, v_begin + q);
+        const int blk_lo = OFFe >> 3, blk_hi = (OFFe + nv + 7) >> 3;
+        const int bw = (blk_hi - blk_lo + FR_ROWS - 1) / FR_ROWS;
+        const int b_begin = blk_lo + wid * bw, b_end = min(blk_hi, b_begin + bw);
         for (int j0 = 0; j0 < Jpad; j0 += 64) {
             const bool two = (j0 + 32) < Jpad;
             float acc[FR_ROWS][2];
 #pragma unroll
             for (int r = 0; r < FR_ROWS; ++r) acc[r][0] = acc[r][1] = 0.f;
-            const float* tt = nt.T1 + (size_t)v_begin * Jpad + j0 + lane;
-#pragma unroll 4
-            for (int v = v_begin; v < v_end; ++v) {
-                const int al = v + OFFe;
-                const int ph = al + (al >> 3);
-                const float t0 = __ldg(tt);
-                const float t1 = two ? __ldg(tt + 32) : 0.f;
-                tt += Jpad;
+            const float* tt = nt.T1 + (ptrdiff_t)(8 * b_begin - OFFe) * Jpad + j0 + lane;
+            const float* eb = s_E + 9 * b_begin;
+            for (int blk = b_begin; blk < b_end; ++blk) {
 #pragma unroll
-                for (int r = 0; r < FR_ROWS; ++r) {
-                    const float xe = s_E[r * a.xlen_e_phys + ph];  // broadcast; rows >= nrows unused
-                    acc[r][0] = fmaf(xe, t0, acc[r][0]);
-                    acc[r][1] = fmaf(xe, t1, acc[r][1]);
+                for (int i = 0; i < 8; ++i) {
+                    const float t0 = __ldg(tt + i * Jpad);
+                    const float t1 = two ? __ldg(tt + i * Jpad + 32) : 0.f;
+#pragma unroll
+                    for (int r = 0; r < FR_ROWS; ++r) {
+                        const float xe = eb[r * a.xlen_e_phys + i];  // broadcast; rows >= nrows unused
+                        acc[r][0] = fmaf(xe, t0, acc[r][0]);
+                        acc[r][1] = fmaf(xe, t1, acc[r][1]);
+                    }
                 }
+                tt += 8 * Jpad;
+                eb += 9;
             }
             // each warp holds the partial sums of its range of v: combine in shared memory as
             // 2^-32 fixed point (|c_j| < 2^30 by far; integer adds commute, so the result does
