@@ -92,6 +92,36 @@ def gaussian_filter(shape, sigma):
     return np.broadcast_to(g, shape).copy()
 
 
+def _row_notch(band_rows: np.ndarray, s: float) -> np.ndarray:
+    """filtering.py:206-215: packed rfft along the last axis, gaussian_filter mask, irfft."""
+    spectrum = fftpack.rfft(band_rows, axis=-1)
+    damp = gaussian_filter(shape=spectrum.shape, sigma=s)
+    return fftpack.irfft(spectrum * damp)
+
+
+def _filter_detail_level(ch, width_fraction, max_threshold, record=None):
+    """One iteration of the level loop, filtering.py:186-219 (only cH is modified)."""
+    energy = ch**2  # :187
+    magnitude = np.sqrt(energy)  # :188
+    otsu_raw = _threshold_otsu(energy)  # :190-192
+    threshold = min(max_threshold, np.sqrt(otsu_raw))  # :193
+    is_fg = magnitude > threshold  # :195
+    fg_part = ch * is_fg  # :196
+    bg_part = ch * (1 - is_fg)  # :197  (1 - bool) is int64 -> float64 from here on
+    row_median = np.median(bg_part, axis=-1)  # :199-202
+    inpainted = bg_part + np.broadcast_to(row_median[..., np.newaxis], ch.shape) * is_fg  # :204
+    n_rows = inpainted.shape[1] if inpainted.ndim == 3 else inpainted.shape[0]  # :208-211
+    s = n_rows * width_fraction  # :213
+    bg_filtered = _row_notch(inpainted, s)  # :206, :214-215
+    result = fg_part + bg_filtered * (1 - is_fg)  # :217
+    if record is not None:
+        record.append(
+            dict(ch=ch, otsu=otsu_raw, threshold=threshold, mask=is_fg, median=row_median, s=s,
+                 background_filtered=bg_filtered, ch_filtered=result)
+        )
+    return result
+
+
 def log_space_fft_filtering(
     input_image,
     wavelet="db3",
@@ -101,68 +131,18 @@ def log_space_fft_filtering(
     _trace: Optional[dict] = None,
 ):
     """filtering.py:139-224.  ``_trace`` (oracle-only) collects per-level intermediates."""
-    input_image_log = np.log(1.0 + input_image)
-    coeffs = _wavedec2(input_image_log, wavelet, level)
-    approx = coeffs[0]
-    detail = coeffs[1:]
-
-    width_fraction = sigma / min(input_image.shape)
-    if len(input_image.shape) == 3:
-        width_fraction = sigma / min(input_image.shape[1:])
-
+    log_image = np.log(1.0 + input_image)  # :175
+    pyramid = _wavedec2(log_image, wavelet, level)  # :176
+    spatial = input_image.shape[1:] if input_image.ndim == 3 else input_image.shape  # :180-183
+    width_fraction = sigma / min(spatial)
+    levels_rec = [] if _trace is not None else None
+    rebuilt = [pyramid[0]]
+    for ch, cv, cd in pyramid[1:]:  # :186
+        rebuilt.append((_filter_detail_level(ch, width_fraction, max_threshold, levels_rec), cv, cd))
+    log_filtered = _waverec2(rebuilt, wavelet)  # :221
     if _trace is not None:
-        _trace["log"] = input_image_log
-        _trace["approx"] = approx
-        _trace["levels"] = []
-
-    coeff_filtered = [approx]
-    for i, (ch, cv, cd) in enumerate(detail):
-        ch_sq = ch**2
-        ch_power = np.sqrt(ch_sq)
-
-        otsu_raw = _threshold_otsu(ch_sq)
-        otsu_threshold_sqrt = np.sqrt(otsu_raw)
-        threshold = min(max_threshold, otsu_threshold_sqrt)
-
-        mask = ch_power > threshold
-        foreground = ch * mask
-        background = ch * (1 - mask)
-
-        background_means = np.broadcast_to(
-            np.median(background, axis=-1)[..., np.newaxis], ch.shape
-        )
-        background_inpainted = background + background_means * mask
-
-        fft = fftpack.rfft(background_inpainted, axis=-1)
-        s_shape = fft.shape[0]
-        if len(fft.shape) == 3:
-            s_shape = fft.shape[1]
-        s = s_shape * width_fraction
-        g = gaussian_filter(shape=fft.shape, sigma=s)
-        background_filtered = fftpack.irfft(fft * g)
-
-        ch_filtered = foreground + background_filtered * (1 - mask)
-        coeff_filtered.append((ch_filtered, cv, cd))
-
-        if _trace is not None:
-            _trace["levels"].append(
-                dict(
-                    ch=ch,
-                    otsu=otsu_raw,
-                    threshold=threshold,
-                    mask=mask,
-                    median=np.median(background, axis=-1),
-                    s=s,
-                    background_filtered=background_filtered,
-                    ch_filtered=ch_filtered,
-                )
-            )
-
-    img_log_filtered = _waverec2(coeff_filtered, wavelet)
-    img_filtered = np.exp(img_log_filtered) + 1.0
-    if _trace is not None:
-        _trace["log_filtered"] = img_log_filtered
-    return img_filtered
+        _trace.update(log=log_image, approx=pyramid[0], levels=levels_rec, log_filtered=log_filtered)
+    return np.exp(log_filtered) + 1.0  # :222  (plus one, as in the reference)
 
 
 def normalize_image(images: List[np.ndarray]) -> np.ndarray:
@@ -196,33 +176,22 @@ def get_hemisphere_flatfield(input_tile_path, tile_config, flatfields, zarr=True
 
 def flatfield_correction(image_tiles, flatfield, darkfield, baseline=None) -> np.ndarray:
     """filtering.py:338-414 (dark subtract with floor at 0, divide by flat, clip, TRUNCATE)."""
-    image_tiles = np.array(image_tiles)
-    if image_tiles.ndim != flatfield.ndim:
-        flatfield = np.expand_dims(flatfield, axis=0)
-    if image_tiles.ndim != darkfield.ndim:
-        darkfield = np.expand_dims(darkfield, axis=0)
-    darkfield = darkfield[: image_tiles.shape[-2], : image_tiles.shape[-1]]
-    if darkfield.shape != image_tiles.shape:
-        raise ValueError(
-            "Please, check the shape of the darkfield. "
-            f"Image: {image_tiles.shape} - Darkfield: {darkfield.shape}"
-        )
-    if flatfield.shape != image_tiles.shape:
-        raise ValueError(
-            "Please, check the shape of the flatfield."
-            f"Image: {image_tiles.shape} - Flatfield: {flatfield.shape}"
-        )
-    if baseline is None:
-        baseline = np.zeros((image_tiles.shape[0],))
-    baseline_indxs = tuple([slice(None)] + ([np.newaxis] * (image_tiles.ndim - 1)))
-    negative_darkfield = np.where(image_tiles <= darkfield)
-    positive_darkfield = np.where(image_tiles > darkfield)
-    image_tiles[negative_darkfield] = 0
-    image_tiles[positive_darkfield] = (
-        image_tiles[positive_darkfield] - darkfield[positive_darkfield]
-    )
-    corrected_tiles = image_tiles / flatfield - baseline[baseline_indxs]
-    return np.clip(corrected_tiles, 0, 65535).astype("uint16")
+    tiles = np.array(image_tiles)  # :369 (copy)
+    flat = flatfield if tiles.ndim == flatfield.ndim else np.expand_dims(flatfield, axis=0)  # :371-372
+    dark = darkfield if tiles.ndim == darkfield.ndim else np.expand_dims(darkfield, axis=0)  # :374-375
+    dark = dark[: tiles.shape[-2], : tiles.shape[-1]]  # :377
+    for name, field in (("darkfield. ", dark), ("flatfield.", flat)):  # :379-391
+        if field.shape != tiles.shape:
+            raise ValueError(
+                f"Please, check the shape of the {name}Image: {tiles.shape} - {name.strip('. ').capitalize()}: {field.shape}"
+            )
+    base = np.zeros((tiles.shape[0],)) if baseline is None else baseline  # :393-394
+    base = base[tuple([slice(None)] + [np.newaxis] * (tiles.ndim - 1))]  # :396
+    below = tiles <= dark  # :399-406: pixels at or under the dark level become 0, the rest lose it
+    tiles[below] = 0
+    tiles[~below] = tiles[~below] - dark[~below]
+    corrected = tiles / flat - base  # :409
+    return np.clip(corrected, 0, 65535).astype("uint16")  # :412 (truncation)
 
 
 def filter_stripes(
