@@ -950,8 +950,7 @@ int dstr_destroy(dstr_ctx* ctx) {
             if (ctx->d_pyr[l][b2]) cudaFree(ctx->d_pyr[l][b2]);
     if (ctx->d_lstat) cudaFree(ctx->d_lstat);
     if (ctx->d_pstat) cudaFree(ctx->d_pstat);
-    if (ctx->d_flat) cudaFree(ctx->d_flat);
-    if (ctx->d_dark) cudaFree(ctx->d_dark);
+    if (ctx->d_flat) cudaFree(ctx->d_flat);  // d_dark lives in the same allocation
     for (int i = 0; i < 2; ++i) {
         if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
         if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
@@ -988,8 +987,11 @@ int dstr_set_flat_dark(dstr_ctx* ctx, const float* flat, const float* dark) {
         return 0;
     }
     const size_t bytes = sizeof(float) * (size_t)ctx->H * ctx->W;
-    if (!ctx->d_flat) CK(ctx, cudaMalloc(&ctx->d_flat, bytes));
-    if (!ctx->d_dark) CK(ctx, cudaMalloc(&ctx->d_dark, bytes));
+    if (!ctx->d_flat) {
+        // one allocation [1/flat | dark]: a single L2 access-policy window can cover both fields
+        CK(ctx, cudaMalloc(&ctx->d_flat, 2 * bytes));
+        ctx->d_dark = ctx->d_flat + (size_t)ctx->H * ctx->W;
+    }
     // the epilogue multiplies by 1/flat (division stays off the device's XU pipe); the
     // reciprocal is rounded once from double, so x * (1/flat) is within 1 ulp of x / flat
     std::vector<float> inv((size_t)ctx->H * ctx->W);
@@ -997,6 +999,27 @@ int dstr_set_flat_dark(dstr_ctx* ctx, const float* flat, const float* dark) {
     CK(ctx, cudaMemcpyAsync(ctx->d_flat, inv.data(), bytes, cudaMemcpyHostToDevice, ctx->s_comp));
     CK(ctx, cudaMemcpyAsync(ctx->d_dark, dark, bytes, cudaMemcpyHostToDevice, ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    {
+        // The two fields are re-read for every plane while GBs of plane data stream through L2:
+        // keep them resident with a persisting access-policy window on the compute stream (the
+        // final synthesis kernel runs there).  Best effort: failures only cost performance.
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+            prop.accessPolicyMaxWindowSize > 0) {
+            const size_t win = std::min<size_t>(2 * bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            const size_t carve = std::min<size_t>(win, (size_t)prop.persistingL2CacheMaxSize);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                cudaStreamAttrValue attr = {};
+                attr.accessPolicyWindow.base_ptr = ctx->d_flat;
+                attr.accessPolicyWindow.num_bytes = win;
+                attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(ctx->s_comp, cudaStreamAttributeAccessPolicyWindow, &attr);
+            }
+            cudaGetLastError();
+        }
+    }
     ctx->have_flat_dark = true;
     return 0;
 }

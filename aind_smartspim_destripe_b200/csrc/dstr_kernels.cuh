@@ -133,7 +133,7 @@ __device__ __forceinline__ void load_pair(const float* p, float& a, float& b) {
 }
 // values already clipped to [0, 65535]
 __device__ __forceinline__ void store_pair(unsigned short* p, float a, float b) {
-    *reinterpret_cast<unsigned*>(p) = f32_to_u16_trunc(a) | (f32_to_u16_trunc(b) << 16);
+    __stcs(reinterpret_cast<unsigned*>(p), f32_to_u16_trunc(a) | (f32_to_u16_trunc(b) << 16));  // final output: streaming
 }
 __device__ __forceinline__ void store_pair(float* p, float a, float b) {
     *reinterpret_cast<float2*>(p) = make_float2(a, b);
