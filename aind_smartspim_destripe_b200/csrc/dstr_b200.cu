@@ -445,6 +445,7 @@ void resolve_timers(dstr_ctx* ctx) {
 template <int EPL>
 int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem, const DispatchParams& dp,
                   cudaStream_t st) {
+    smem += sizeof(unsigned) * FR_ROWS * EPL;  // mask bit words
     // opt in to the full dynamic shared memory once per instantiation and device (never lowered, so
     // concurrent contexts in other host threads cannot invalidate each other's launches)
     static std::mutex mtx;

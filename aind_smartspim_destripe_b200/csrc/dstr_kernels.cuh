@@ -952,6 +952,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // then converted to float
     unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * a.xlen_o_phys);  // [FR_ROWS][Jpad_max]
     float* s_c = reinterpret_cast<float*>(s_c64 + FR_ROWS * a.Jpad_max);                                // [FR_ROWS][Jpad_max]
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_c + FR_ROWS * a.Jpad_max);                         // [FR_ROWS][EPL] mask bits
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int z = blockIdx.y;
@@ -977,11 +978,15 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
         for (int i = 0; i < EPL; ++i) {
             const int e = lane + 32 * i;
             key[i] = 0xffffffffu;
+            bool m = false;
             if (e < n) {
                 const float c = grow[e];
-                const bool m = __fmul_rn(c, c) > thr_q;
+                m = __fmul_rn(c, c) > thr_q;
                 key[i] = f2key(m ? 0.0f : (c + 0.0f));  // zero-filled background, canonical +0
             }
+            // mask bits of elements 32i .. 32i+31, kept for the output stage
+            const unsigned mbits = __ballot_sync(0xffffffffu, m);
+            if (lane == 0) s_mask[wid * EPL + i] = mbits;
         }
         // ---- exact median of the zero-filled background (np.median, filtering.py:201) -------
         // Order statistics k1 = (n-1)/2 and k2 = n/2 of the keys.  The masked entries are exact
@@ -1156,19 +1161,19 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 ye[7] = fmaf(c, u1.w, ye[7]);
             }
         }
-        // dH[t] = masked ? 0 : -(B x)[t]; the mask is re-derived from the coefficient about to be
-        // overwritten (each element is read and written by this thread only)
+        // dH[t] = masked ? 0 : -(B x)[t]; mask bits come from the selection phase
         float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + r) * a.pitch;
+        const unsigned* mrow = s_mask + r * EPL;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int t = 8 * seg + i;
             if (t <= nh) {
-                const float c = orow[t];
-                orow[t] = (__fmul_rn(c, c) > thr_q) ? 0.f : -(ye[i] + yo[i]);
+                const bool mt = (mrow[t >> 5] >> (t & 31)) & 1u;
+                orow[t] = mt ? 0.f : -(ye[i] + yo[i]);
                 const int tm = n - t;
                 if (t != 0 && tm != t) {
-                    const float cm = orow[tm];
-                    orow[tm] = (__fmul_rn(cm, cm) > thr_q) ? 0.f : -(ye[i] - yo[i]);
+                    const bool mm = (mrow[tm >> 5] >> (tm & 31)) & 1u;
+                    orow[tm] = mm ? 0.f : -(ye[i] - yo[i]);
                 }
             }
         }
