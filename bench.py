@@ -82,60 +82,86 @@ def recorded_traffic(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    """SM clock / throttle-reason sampling during the timed region: an NVML polling thread
+    (about 1 ms per sample; the recipe's ``nvidia-smi --query-gpu=clocks.sm,...`` line is the
+    fallback when NVML cannot be loaded)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.samples = []  # (sm_mhz, reasons bitmask-as-names)
+        self.sm_max = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            import torch
+
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.device).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(self.device))
+
+    def _poll_nvml(self, nv, h):
+        bits = [(nv.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(mhz), [nm for bit, nm in bits if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                self.samples.append((float(parts[0]),
+                                     [nm for nm, v in zip(self.NAMES, parts[2:6]) if v.lower().startswith("active")]))
+                self.sm_max = float(parts[1])
+            except Exception:
+                time.sleep(0.01)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            nv, h = self._nvml_handle()
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._poll_smi, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["sampler not started"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+        sm = [s[0] for s in self.samples]
+        reasons = sorted({r for s in self.samples for r in s[1]})
         return {
             "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
+            "sm_max_mhz": self.sm_max,
             "samples": len(sm),
-            "reasons": sorted(reasons),
+            "source": self.source,
+            "reasons": reasons,
         }
 
 

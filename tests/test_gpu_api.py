@@ -194,3 +194,47 @@ def test_downscale_and_fused_pyramid_match_oracle(production_configs):
     np.testing.assert_array_equal(p1, ref[1])
     np.testing.assert_array_equal(p2, ref[2])
     np.testing.assert_array_equal(out, fl.filter_planes(st, "0_0", no_cells, cells, shadow, 2500))
+
+
+@pytest.mark.parametrize("with_shadow", [False, True])
+def test_batch_filter_directory_matches_oracle(tmp_path, production_configs, with_shadow):
+    # /root/reference/code/aind_smartspim_destripe/destriper.py:267-378 (TIFF / RAW directory path)
+    import struct
+
+    from aind_smartspim_destripe_b200 import destriper as D
+
+    no_cells, cells = production_configs
+    H, W = 160, 192
+    src, dst = tmp_path / "in", tmp_path / "out"
+    tile = src / "Ex_488_Em_525" / "471320" / "471320_304840"
+    tile.mkdir(parents=True)
+    (src / "metadata.txt").write_text("acquisition")
+    st = S.synthetic_stack(5, H, W, cells_every=2)
+    small = S.synthetic_stack(1, 96, 112)[0]
+    names = []
+    for z in range(4):
+        D._tiff_write(str(tile / f"{z:06d}.tiff"), st[z])
+        names.append(tile / f"{z:06d}.tiff")
+    with open(tile / "000004.raw", "wb") as fp:  # big-endian raw, like the acquisition software
+        fp.write(struct.pack(">II", H, W))
+        fp.write(st[4].astype(">u2").tobytes())
+    names.append(tile / "000004.raw")
+    D._tiff_write(str(tile / "000005.tiff"), small)  # different shape inside one batch
+    names.append(tile / "000005.tiff")
+    (tile / "000006.tiff").write_bytes(b"garbage")
+    shadow = _shadow(H, W) if with_shadow else None
+    if with_shadow:
+        (tile / "000005.tiff").unlink()  # the flat field only fits the (H, W) planes
+        names.pop()
+    D.batch_filter(src, dst, workers=3, chunks=4, high_int_filt_params=cells, low_int_filt_params=no_cells,
+                   shadow_correction=shadow)
+    assert (dst / "metadata.txt").read_text() == "acquisition"
+    assert str(tile / "000006.tiff") in (dst / "destripe_log.txt").read_text()
+    for p in names:
+        img = np.asarray(D.imread(p))
+        out = D.imread((dst / p.relative_to(src)).with_suffix(".tiff"))
+        ref = OF.filter_stripes(img.astype(np.float32), str(p), no_cells, cells, shadow, 2700)
+        ref = np.clip(ref, 0, 65535).astype(np.uint16)
+        assert out.dtype == np.uint16 and out.shape == img.shape
+        frac, worst, _ = u16_agreement(out, ref)
+        assert frac >= U16_FRACTION, (p.name, frac, worst)
