@@ -283,6 +283,7 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
     std::vector<double> hb;
     idft_even(n, b, ct, hb);
     const int nhp8 = (nh + 1 + 7) & ~7;
+    const int nhp64 = (nhp8 + 63) & ~63;
     const int nhp4 = (nh + 4) & ~3;
 
     // dense fallback: exact kernels of full circular length
@@ -343,7 +344,7 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
     out.J = J;
     out.Jpad = (J + 31) & ~31;
     out.T1.assign((size_t)(nhp4 + 16) * out.Jpad, 0.f);  // 8 zero rows of margin before v = 0 and after v = nh
-    out.T2.assign((size_t)std::max(J, 1) * nhp8, 0.f);
+    out.T2.assign((size_t)std::max(J, 1) * nhp64, 0.f);
     for (int j = 0; j < J; ++j) {
         const double r = a[j] - best_G[j];
         const double rho = ((j == 0) ? 1.0 : 2.0) * r / n;  // J < n/2: no Nyquist mode here
@@ -351,7 +352,11 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
             const double omega = (v == 0 || (n % 2 == 0 && v == nh)) ? 1.0 : 2.0;
             const double c = ct[(int)(((long long)j * v) % n)];
             out.T1[(size_t)(v + 8) * out.Jpad + j] = (float)(omega * c);
-            out.T2[(size_t)j * nhp8 + v] = (float)(rho * c);
+            // row layout: groups of 8 segments (64 outputs); first the float4 of outputs 0..3 of each of
+            // the 8 segments, then the float4 of outputs 4..7 (a warp's load is 128 contiguous bytes)
+            const int seg = v >> 3, k = v & 7;
+            const size_t off = (size_t)(seg >> 3) * 64 + (size_t)(k >> 2) * 32 + (size_t)(seg & 7) * 4 + (k & 3);
+            out.T2[(size_t)j * nhp64 + off] = (float)(rho * c);
         }
     }
 }
@@ -365,9 +370,9 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     const double s = (double)Hl * ((double)sigma / (double)std::min(ctx->H, ctx->W));
     NotchHost hst;
     design_notch(n, s, ctx->notch_eps, hst);
-    auto pad4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
-    const size_t o_te = 0, o_to = o_te + pad4(hst.te.size()), o_T1 = o_to + pad4(hst.to.size()),
-                 o_T2 = o_T1 + pad4(hst.T1.size()), total = o_T2 + pad4(hst.T2.size());
+    auto pad32 = [](size_t v) { return (v + 31) & ~(size_t)31; };  // 128-byte aligned sub-tables
+    const size_t o_te = 0, o_to = o_te + pad32(hst.te.size()), o_T1 = o_to + pad32(hst.to.size()),
+                 o_T2 = o_T1 + pad32(hst.T1.size()), total = o_T2 + pad32(hst.T2.size());
     std::vector<float> host(total, 0.f);
     std::copy(hst.te.begin(), hst.te.end(), host.begin() + o_te);
     std::copy(hst.to.begin(), hst.to.end(), host.begin() + o_to);
@@ -581,11 +586,16 @@ int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
     fa.ntap_e_max = std::max(fa.nt[0].ntap_e, fa.nt[1].ntap_e);
     fa.ntap_o_max = std::max(fa.nt[0].ntap_o, fa.nt[1].ntap_o);
     fa.Jpad_max = std::max(fa.nt[0].Jpad, fa.nt[1].Jpad);
-    fa.xlen_e_phys = (fa.nhp8 + fa.ntap_e_max) / 8 * 9;
-    fa.xlen_o_phys = (fa.nhp8 + fa.ntap_o_max) / 8 * 9;
+    fa.nhp64 = (fa.nhp8 + 63) & ~63;
+    // row strides = 8 (mod 16) words: with the 9-word segment stride the 8 segments x 4 rows of a warp
+    // fall into 32 distinct banks
+    auto bank_pad = [](int v) { return v + ((8 - v) & 15); };
+    fa.xlen_e_phys = bank_pad((fa.nhp8 + fa.ntap_e_max) / 8 * 9);
+    fa.xlen_o_phys = bank_pad((fa.nhp8 + fa.ntap_o_max) / 8 * 9);
     const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
                                          (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
-                                         (size_t)3 * FR_ROWS * fa.Jpad_max);  // 64-bit accumulators + float copy
+                                         (size_t)3 * FR_ROWS * fa.Jpad_max +  // 64-bit accumulators + float copy
+                                         (size_t)8 * FR_ROWS);                // row padding of the float copy
     if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
     const int epl = (g.W + 31) / 32;
     if (epl <= 2) return launch_filter<2>(ctx, fa, P.z, smem, P.dp, st);
@@ -1358,7 +1368,11 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
     NotchHost h;
     design_notch(n, s, eps, h);
     const int nh = n / 2;
-    const int nhp8 = (nh + 1 + 7) & ~7;
+    const int nhp64 = (((nh + 1 + 7) & ~7) + 63) & ~63;
+    auto t2_off = [](int t) {  // the device layout of a T2 row (design_notch)
+        const int seg = t >> 3, k = t & 7;
+        return (size_t)(seg >> 3) * 64 + (size_t)(k >> 2) * 32 + (size_t)(seg & 7) * 4 + (k & 3);
+    };
     std::vector<double> xe(n), xo(n);
     for (int t = 0; t < n; ++t) {
         const int tr = (t == 0) ? 0 : n - t;
@@ -1372,7 +1386,7 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
         double ye = 0.0, yo = 0.0;
         for (int k = 0; k < h.ntap_e; ++k) ye += (double)h.te[k] * xe[(((t - (h.ue_lo + k)) % n) + n) % n];
         for (int k = 0; k < h.ntap_o; ++k) yo += (double)h.to[k] * xo[(((t - (h.uo_lo + k)) % n) + n) % n];
-        for (int j = 0; j < h.J; ++j) ye += c[j] * (double)h.T2[(size_t)j * nhp8 + t];
+        for (int j = 0; j < h.J; ++j) ye += c[j] * (double)h.T2[(size_t)j * nhp64 + t2_off(t)];
         y[t] = ye + yo;
         const int tm = n - t;
         if (t != 0 && tm != t) y[tm] = ye - yo;

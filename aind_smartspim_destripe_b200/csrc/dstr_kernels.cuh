@@ -921,7 +921,8 @@ struct NotchTables {
     const float* te;  // even-part FIR taps [ntap_e]; tap k <-> circular offset u = ue_lo + k
     const float* to;  // odd-part FIR taps  [ntap_o]; tap k <-> u = uo_lo + k
     const float* T1;  // [nhp4][Jpad]  omega_v cos(2 pi j v / n)   (v-major)
-    const float* T2;  // [J][nhp8]     rho_j   cos(2 pi j t / n)   (j-major)
+    const float* T2;  // [J][nhp64]    rho_j   cos(2 pi j t / n)   (j-major; inside a row the two float4
+                      //               halves of 8 consecutive 8-output segments are grouped: see t2_offset)
     int ntap_e, ue_lo, ntap_o, uo_lo, J, Jpad;
 };
 
@@ -935,7 +936,8 @@ struct FilterLevelArgs {
     int nh;             // n / 2: the half range is t = 0..nh
     int nhp8;           // nh + 1 rounded up to a multiple of 8
     int n_pad8;
-    int xlen_e_phys, xlen_o_phys;  // per-row physical floats (max over the two configs)
+    int nhp64;          // T2 row stride: nhp8 rounded up to a multiple of 64
+    int xlen_e_phys, xlen_o_phys;  // per-row physical floats (max over the two configs), = 8 mod 16
     int ntap_e_max, ntap_o_max, Jpad_max;
 };
 
@@ -951,8 +953,9 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // rank-J coefficients: accumulated as 64-bit fixed point (deterministic, order-free atomics),
     // then converted to float
     unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * a.xlen_o_phys);  // [FR_ROWS][Jpad_max]
-    float* s_c = reinterpret_cast<float*>(s_c64 + FR_ROWS * a.Jpad_max);                                // [FR_ROWS][Jpad_max]
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_c + FR_ROWS * a.Jpad_max);                         // [FR_ROWS][EPL] mask bits
+    float* s_c = reinterpret_cast<float*>(s_c64 + FR_ROWS * a.Jpad_max);                                // [FR_ROWS][Jpad_max + 8]
+    const int cstride = a.Jpad_max + 8;  // rows 8 banks apart: the 4 rows' c_j are read in one wavefront
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_c + FR_ROWS * cstride);                            // [FR_ROWS][EPL] mask bits
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int z = blockIdx.y;
@@ -1126,30 +1129,37 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             }
         }
         __syncthreads();
-        for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS)
-            s_c[i] = __ll2float_rn((long long)s_c64[i]) * (1.0f / 4294967296.0f);
+        for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS) {
+            const int r = i / a.Jpad_max;
+            s_c[r * cstride + (i - r * a.Jpad_max)] = __ll2float_rn((long long)s_c64[i]) * (1.0f / 4294967296.0f);
+        }
         __syncthreads();
     }
 
-    // ---- register-tiled FIRs + rank-J correction over (row, 8-output segment) pairs -----------
+    // ---- register-tiled FIRs + rank-J correction over (8-output segment, row) pairs -----------
+    // The row index runs fastest: a warp covers 8 segments x FR_ROWS rows, so its T2 loads touch
+    // 8 x 16 contiguous bytes (broadcast over the rows) and the rows' E / O windows sit in
+    // different banks (row strides = 8 mod 16 words, segment stride 9 words).
     const int nseg = a.nhp8 >> 3;
-    for (int w = tid; w < nrows * nseg; w += FR_THREADS) {
-        const int r = w / nseg;
-        const int seg = w - r * nseg;
+    for (int w = tid; w < FR_ROWS * nseg; w += FR_THREADS) {
+        const int seg = w / FR_ROWS;
+        const int r = w - seg * FR_ROWS;
+        if (r >= nrows) continue;
         float ye[8], yo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ye[i] = yo[i] = 0.f;
         fir8(ye, s_E + r * a.xlen_e_phys, s_te, nt.ntap_e, seg + (nt.ntap_e >> 3));
         fir8(yo, s_O + r * a.xlen_o_phys, s_to, nt.ntap_o, seg + (nt.ntap_o >> 3));
         if (nt.J > 0) {
-            const float* cp = s_c + r * a.Jpad_max;
-            const float4* t2 = reinterpret_cast<const float4*>(nt.T2 + 8 * seg);
-            const int stride4 = a.nhp8 >> 2;
+            const float* cp = s_c + r * cstride;
+            // outputs 8 seg .. 8 seg + 3 at float4 index 16 (seg / 8) + seg % 8, the next four 8 further
+            const float4* t2 = reinterpret_cast<const float4*>(nt.T2) + 16 * (seg >> 3) + (seg & 7);
+            const int stride4 = a.nhp64 >> 2;
 #pragma unroll 4
             for (int j = 0; j < nt.J; ++j) {
                 const float c = cp[j];
                 const float4 u0 = __ldg(t2);
-                const float4 u1 = __ldg(t2 + 1);
+                const float4 u1 = __ldg(t2 + 8);
                 t2 += stride4;
                 ye[0] = fmaf(c, u0.x, ye[0]);
                 ye[1] = fmaf(c, u0.y, ye[1]);
