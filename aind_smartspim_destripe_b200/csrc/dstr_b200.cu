@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -268,6 +269,20 @@ void pack_taps(int n, const std::vector<double>& h, int R, bool dense, std::vect
     }
 }
 
+// cost-model weights (overridable for experiments: DSTR_NOTCH_COST_J / DSTR_NOTCH_COST_JPAD)
+double env_or(const char* name, double dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atof(v) : dflt;
+}
+double notch_cost_j() {
+    static const double v = env_or("DSTR_NOTCH_COST_J", 3.0);
+    return v;
+}
+double notch_cost_jpad() {
+    static const double v = env_or("DSTR_NOTCH_COST_JPAD", 2.0);
+    return v;
+}
+
 void design_notch(int n, double s, double eps, NotchHost& out) {
     const int nh = n / 2;
     const int Jn = (n % 2 == 0) ? nh + 1 : (n + 1) / 2;  // cosine modes j = 0..Jn-1
@@ -316,7 +331,10 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
                 J = j;
             }
             if (2 * RG + 1 >= n || 2 * Rb + 1 >= n || J >= nh) continue;
-            const double cost = (double)(((2 * RG + 1 + 7) & ~7) + ((2 * Rb + 1 + 7) & ~7)) + 2.5 * J;
+            // work in units of one FIR tap: the rank-J stages issue more loads per FMA than the
+            // register-tiled FIR (cost per mode ~3), and the projection runs on 32-lane groups of modes
+            const double cost = (double)(((2 * RG + 1 + 7) & ~7) + ((2 * Rb + 1 + 7) & ~7)) +
+                                notch_cost_j() * J + notch_cost_jpad() * ((J + 31) & ~31);
             if (cost < best_cost) {
                 best_cost = cost;
                 hybrid = true;

@@ -896,24 +896,48 @@ __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float(b);
 }
 
-// acc[i] += sum_k taps[k] * Xlog[8*m0 + i - k],  k = 0..ntap-1 (ntap % 8 == 0)
+// acc[i] += sum_k taps[k] * Xlog[8*m0 + i - k],  k = 0..ntap-1 (ntap % 8 == 0).
+// Logical element a = 8 b + i lives at Xphys[BS * b + ES * i]  (padded rows: ES 1, BS 9).
+template <int ES, int BS>
 __device__ __forceinline__ void fir8(float (&acc)[8], const float* __restrict__ Xphys,
                                      const float* __restrict__ taps, int ntap, int m0) {
-    const float* Xp = Xphys + 9 * m0;
+    const float* Xp = Xphys + BS * m0;
     float w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = Xp[i];
+    for (int i = 0; i < 8; ++i) w[i] = Xp[ES * i];
     const float4* t4 = reinterpret_cast<const float4*>(taps);
     for (int kk = 0; kk < ntap / 8; ++kk) {
         const float4 ta = t4[2 * kk], tb = t4[2 * kk + 1];
         const float tk[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-        Xp -= 9;
+        Xp -= BS;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(tk[k], w[(i - k) & 7], acc[i]);
-            w[7 - k] = Xp[7 - k];
+            w[7 - k] = Xp[ES * (7 - k)];
         }
+    }
+}
+
+// Partial sums of c_j = sum_v T1[v][j] x_e[v] over the 8-element blocks [0, nblk) starting at eb / tt,
+// for all rows of the block at once (broadcast reads of x_e) and lanes j (and j + 32 when TWO).
+template <bool TWO, int ROWS>
+__device__ __forceinline__ void lr1_partial(const float* __restrict__ tt, const float* __restrict__ eb,
+                                            int row_stride, int nblk, int Jpad, float (&acc)[ROWS][2]) {
+    for (int blk = 0; blk < nblk; ++blk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float t0 = __ldg(tt + i * Jpad);
+            const float t1 = TWO ? __ldg(tt + i * Jpad + 32) : 0.f;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const float xe = eb[r * row_stride + i];
+                acc[r][0] = fmaf(xe, t0, acc[r][0]);
+                if (TWO) acc[r][1] = fmaf(xe, t1, acc[r][1]);
+            }
+        }
+        tt += 8 * Jpad;
+        eb += 9;
     }
 }
 
@@ -1102,22 +1126,11 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
 #pragma unroll
             for (int r = 0; r < FR_ROWS; ++r) acc[r][0] = acc[r][1] = 0.f;
             const float* tt = nt.T1 + (ptrdiff_t)(8 * b_begin - OFFe) * Jpad + j0 + lane;
-            const float* eb = s_E + 9 * b_begin;
-            for (int blk = b_begin; blk < b_end; ++blk) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float t0 = __ldg(tt + i * Jpad);
-                    const float t1 = two ? __ldg(tt + i * Jpad + 32) : 0.f;
-#pragma unroll
-                    for (int r = 0; r < FR_ROWS; ++r) {
-                        const float xe = eb[r * a.xlen_e_phys + i];  // broadcast; rows >= nrows unused
-                        acc[r][0] = fmaf(xe, t0, acc[r][0]);
-                        acc[r][1] = fmaf(xe, t1, acc[r][1]);
-                    }
-                }
-                tt += 8 * Jpad;
-                eb += 9;
-            }
+            const float* eb = s_E + 9 * b_begin;  // rows >= nrows: unused garbage
+            if (two)
+                lr1_partial<true, FR_ROWS>(tt, eb, a.xlen_e_phys, b_end - b_begin, Jpad, acc);
+            else
+                lr1_partial<false, FR_ROWS>(tt, eb, a.xlen_e_phys, b_end - b_begin, Jpad, acc);
             // each warp holds the partial sums of its range of v: combine in shared memory as
             // 2^-32 fixed point (|c_j| < 2^30 by far; integer adds commute, so the result does
             // not depend on the order in which the warps arrive)
@@ -1148,8 +1161,8 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
         float ye[8], yo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ye[i] = yo[i] = 0.f;
-        fir8(ye, s_E + r * a.xlen_e_phys, s_te, nt.ntap_e, seg + (nt.ntap_e >> 3));
-        fir8(yo, s_O + r * a.xlen_o_phys, s_to, nt.ntap_o, seg + (nt.ntap_o >> 3));
+        fir8<1, 9>(ye, s_E + r * a.xlen_e_phys, s_te, nt.ntap_e, seg + (nt.ntap_e >> 3));
+        fir8<1, 9>(yo, s_O + r * a.xlen_o_phys, s_to, nt.ntap_o, seg + (nt.ntap_o >> 3));
         if (nt.J > 0) {
             const float* cp = s_c + r * cstride;
             // outputs 8 seg .. 8 seg + 3 at float4 index 16 (seg / 8) + seg % 8, the next four 8 further
