@@ -65,6 +65,7 @@ struct TimerSpan {
 
 struct dstr_ctx {
     int device = 0;
+    int sm_count = 148;
     int zcap = 0;
     int H = 0, W = 0;
     int Lmax = 0;    // pywt.dwtn_max_level of the plane shape (what level=None means)
@@ -605,6 +606,17 @@ int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
     fa.ntap_o_max = std::max(fa.nt[0].ntap_o, fa.nt[1].ntap_o);
     fa.Jpad_max = std::max(fa.nt[0].Jpad, fa.nt[1].Jpad);
     fa.nhp64 = (fa.nhp8 + 63) & ~63;
+    {
+        // one wave of resident blocks ahead (8 blocks per SM); DSTR_FILTER_PREFETCH overrides (0 = off)
+        static const int pf = (int)env_or("DSTR_FILTER_PREFETCH", -1.0);
+        fa.prefetch_blocks = pf >= 0 ? pf : 8 * ctx->sm_count;
+        if ((g.pitch * 4) % 16 != 0) fa.prefetch_blocks = 0;
+    }
+    fa.vec_ok = (g.pitch % 4 == 0) && (g.pstride % 4 == 0) && (reinterpret_cast<uintptr_t>(fa.cH) % 16 == 0);
+    fa.ablate = 0;
+#ifdef DSTR_ABLATION
+    fa.ablate = (int)env_or("DSTR_ABLATE", 0.0);
+#endif
     // row strides = 8 (mod 16) words: with the 9-word segment stride the 8 segments x 4 rows of a warp
     // fall into 32 distinct banks
     auto bank_pad = [](int v) { return v + ((8 - v) & 15); };
@@ -612,7 +624,8 @@ int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
     fa.xlen_o_phys = bank_pad((fa.nhp8 + fa.ntap_o_max) / 8 * 9);
     const size_t smem = sizeof(float) * ((size_t)fa.ntap_e_max + fa.ntap_o_max +
                                          (size_t)FR_ROWS * (fa.xlen_e_phys + fa.xlen_o_phys) +
-                                         (size_t)3 * FR_ROWS * fa.Jpad_max +  // 64-bit accumulators + float copy
+                                         (size_t)2 * std::max(FR_ROWS * fa.Jpad_max, 128) +  // 64-bit accumulators (>= 1 KB: reused as store staging)
+                                         (size_t)FR_ROWS * fa.Jpad_max +                     // float copy
                                          (size_t)8 * FR_ROWS);                // row padding of the float copy
     if (smem > 227 * 1024) return fail(ctx, DSTR_E_SHAPE, "row too long for filter kernel");
     const int epl = (g.W + 31) / 32;
@@ -921,6 +934,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         }                                                                                 \
     } while (0)
     CKC(cudaSetDevice(device));
+    CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->geom[0] = {H, W, W, (size_t)H * W};
     for (int l = 1; l <= ctx->Lalloc; ++l) {
         LevelGeom g;

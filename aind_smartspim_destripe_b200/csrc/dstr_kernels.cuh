@@ -963,6 +963,9 @@ struct FilterLevelArgs {
     int nhp64;          // T2 row stride: nhp8 rounded up to a multiple of 64
     int xlen_e_phys, xlen_o_phys;  // per-row physical floats (max over the two configs), = 8 mod 16
     int ntap_e_max, ntap_o_max, Jpad_max;
+    int vec_ok;           // rows are 16-byte aligned: float4 stores allowed
+    int prefetch_blocks;  // rows of the block this many blocks ahead are prefetched into L2 (0 = off)
+    int ablate;  // DSTR_ABLATION builds only (timing experiments): 1 median, 2 projection, 4 expansion, 8 even FIR, 16 odd FIR
 };
 
 template <int EPL>
@@ -977,14 +980,30 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // rank-J coefficients: accumulated as 64-bit fixed point (deterministic, order-free atomics),
     // then converted to float
     unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * a.xlen_o_phys);  // [FR_ROWS][Jpad_max]
-    float* s_c = reinterpret_cast<float*>(s_c64 + FR_ROWS * a.Jpad_max);                                // [FR_ROWS][Jpad_max + 8]
+    float* s_c = reinterpret_cast<float*>(s_c64 + max(FR_ROWS * a.Jpad_max, 128));                      // [FR_ROWS][Jpad_max + 8]
     const int cstride = a.Jpad_max + 8;  // rows 8 banks apart: the 4 rows' c_j are read in one wavefront
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_c + FR_ROWS * cstride);                            // [FR_ROWS][EPL] mask bits
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#ifdef DSTR_ABLATION
+    const int abl = a.ablate;
+#else
+    constexpr int abl = 0;
+#endif
     const int z = blockIdx.y;
     const int row0 = blockIdx.x * FR_ROWS;
     const int nrows = min(FR_ROWS, a.Hl - row0);
+    // The blocks resident on the GPU hold ~19 MB of rows; asking L2 for the rows of the block that
+    // will run in this slot one wave later turns the DRAM round trips of the load phase into L2 hits.
+    if (a.prefetch_blocks > 0 && lane == 0) {
+        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_blocks;
+        const int pz = (int)(lin / gridDim.x);
+        const int prow = (int)(lin - (long long)pz * gridDim.x) * FR_ROWS + wid;
+        if (pz < (int)gridDim.y && prow < a.Hl) {
+            const float* pp = a.cH + (size_t)pz * a.pstride + (size_t)prow * a.pitch;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(a.pitch * 4) : "memory");
+        }
+    }
     const int cfg = plane_uses_cells(pstat[z], dp);
     const NotchTables nt = cfg ? a.nt[1] : a.nt[0];
     // mask rule sqrt(c*c) > thr evaluated as c*c > thr_q (bit-identical, see otsu_kernel)
@@ -1031,7 +1050,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
         cneg = __reduce_add_sync(0xffffffffu, cneg);
         cle0 = __reduce_add_sync(0xffffffffu, cle0);
         float med;
-        if (cneg <= k1 && k2 < cle0) {
+        if ((cneg <= k1 && k2 < cle0) || (abl & 1)) {
             med = 0.f;
         } else {
             unsigned res;
@@ -1093,7 +1112,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             int t = (tau_lo + lane) % n;
             if (t < 0) t += n;
             const int step = 32 % n;
-            for (int tau = tau_lo + lane; tau < tau_hi; tau += 32) {
+            for (int tau = tau_lo + lane; tau < tau_hi && !(abl & 64); tau += 32) {
                 const int tr = (t == 0) ? 0 : n - t;
                 const float c1 = grow[t], c2 = grow[tr];
                 const float x1 = (__fmul_rn(c1, c1) > thr_q) ? med : c1;
@@ -1113,7 +1132,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // 8-element blocks of the padded layout (immediate offsets inside a block); warp w takes the
     // w-th quarter of the blocks for all rows.  T1 carries 8 zero rows before v = 0 and after
     // v = nh, so the partial first / last blocks need no predicates.
-    if (nt.J > 0) {
+    if (nt.J > 0 && !(abl & 2)) {
         const int OFFe = nt.ue_lo + nt.ntap_e;
         const int Jpad = nt.Jpad;
         const int nv = nh + 1;
@@ -1154,50 +1173,114 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // 8 x 16 contiguous bytes (broadcast over the rows) and the rows' E / O windows sit in
     // different banks (row strides = 8 mod 16 words, segment stride 9 words).
     const int nseg = a.nhp8 >> 3;
-    for (int w = tid; w < FR_ROWS * nseg; w += FR_THREADS) {
+    const int total = FR_ROWS * nseg;
+    float* stage = reinterpret_cast<float*>(s_c64) + wid * 64;  // free after the c_j conversion; >= 1 KB
+    for (int w0 = wid * 32; w0 < total; w0 += FR_THREADS) {  // warp-uniform: the stores are warp-collective
+        const int w = w0 + lane;
         const int seg = w / FR_ROWS;
         const int r = w - seg * FR_ROWS;
-        if (r >= nrows) continue;
+        const bool active = (w < total) && (r < nrows);
         float ye[8], yo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ye[i] = yo[i] = 0.f;
-        fir8<1, 9>(ye, s_E + r * a.xlen_e_phys, s_te, nt.ntap_e, seg + (nt.ntap_e >> 3));
-        fir8<1, 9>(yo, s_O + r * a.xlen_o_phys, s_to, nt.ntap_o, seg + (nt.ntap_o >> 3));
-        if (nt.J > 0) {
-            const float* cp = s_c + r * cstride;
-            // outputs 8 seg .. 8 seg + 3 at float4 index 16 (seg / 8) + seg % 8, the next four 8 further
-            const float4* t2 = reinterpret_cast<const float4*>(nt.T2) + 16 * (seg >> 3) + (seg & 7);
-            const int stride4 = a.nhp64 >> 2;
+        if (active) {
+            if (!(abl & 8)) fir8<1, 9>(ye, s_E + r * a.xlen_e_phys, s_te, nt.ntap_e, seg + (nt.ntap_e >> 3));
+            if (!(abl & 16)) fir8<1, 9>(yo, s_O + r * a.xlen_o_phys, s_to, nt.ntap_o, seg + (nt.ntap_o >> 3));
+            if (nt.J > 0 && !(abl & 4)) {
+                const float* cp = s_c + r * cstride;
+                // outputs 8 seg .. 8 seg + 3 at float4 index 16 (seg / 8) + seg % 8, the next four 8 further
+                const float4* t2 = reinterpret_cast<const float4*>(nt.T2) + 16 * (seg >> 3) + (seg & 7);
+                const int stride4 = a.nhp64 >> 2;
 #pragma unroll 4
-            for (int j = 0; j < nt.J; ++j) {
-                const float c = cp[j];
-                const float4 u0 = __ldg(t2);
-                const float4 u1 = __ldg(t2 + 8);
-                t2 += stride4;
-                ye[0] = fmaf(c, u0.x, ye[0]);
-                ye[1] = fmaf(c, u0.y, ye[1]);
-                ye[2] = fmaf(c, u0.z, ye[2]);
-                ye[3] = fmaf(c, u0.w, ye[3]);
-                ye[4] = fmaf(c, u1.x, ye[4]);
-                ye[5] = fmaf(c, u1.y, ye[5]);
-                ye[6] = fmaf(c, u1.z, ye[6]);
-                ye[7] = fmaf(c, u1.w, ye[7]);
+                for (int j = 0; j < nt.J; ++j) {
+                    const float c = cp[j];
+                    const float4 u0 = __ldg(t2);
+                    const float4 u1 = __ldg(t2 + 8);
+                    t2 += stride4;
+                    ye[0] = fmaf(c, u0.x, ye[0]);
+                    ye[1] = fmaf(c, u0.y, ye[1]);
+                    ye[2] = fmaf(c, u0.z, ye[2]);
+                    ye[3] = fmaf(c, u0.w, ye[3]);
+                    ye[4] = fmaf(c, u1.x, ye[4]);
+                    ye[5] = fmaf(c, u1.y, ye[5]);
+                    ye[6] = fmaf(c, u1.z, ye[6]);
+                    ye[7] = fmaf(c, u1.w, ye[7]);
+                }
             }
         }
-        // dH[t] = masked ? 0 : -(B x)[t]; mask bits come from the selection phase
-        float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + r) * a.pitch;
-        const unsigned* mrow = s_mask + r * EPL;
+        if (abl & 32) continue;
+        // ---- dH[t] = masked ? 0 : -(B x)[t], t = 8 seg + i (direct half) and n - t (mirrored half);
+        //      mask bits come from the selection phase -------------------------------------------
+        const int t0 = 8 * seg;
+        float vd[8], vm[8];
+        if (active) {
+            const unsigned* mrow = s_mask + r * EPL;
+            const unsigned dbits = mrow[t0 >> 5] >> (t0 & 31);  // bit i <-> t0 + i (t0 % 8 == 0: one word)
+            // bits of n - t0 - 7 .. n - t0 (bit 7 - i <-> n - t0 - i); entries below 0 are never stored
+            const int lo = n - t0 - 7, loc = max(lo, 0);
+            const int wi = loc >> 5;
+            const unsigned mbits = __funnelshift_r(mrow[wi], mrow[min(wi + 1, EPL - 1)], loc & 31) << (loc - lo);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int t = 8 * seg + i;
-            if (t <= nh) {
-                const bool mt = (mrow[t >> 5] >> (t & 31)) & 1u;
-                orow[t] = mt ? 0.f : -(ye[i] + yo[i]);
-                const int tm = n - t;
-                if (t != 0 && tm != t) {
-                    const bool mm = (mrow[tm >> 5] >> (tm & 31)) & 1u;
-                    orow[tm] = mm ? 0.f : -(ye[i] - yo[i]);
+            for (int i = 0; i < 8; ++i) {
+                vd[i] = ((dbits >> i) & 1u) ? 0.f : -(ye[i] + yo[i]);
+                vm[i] = ((mbits >> (7 - i)) & 1u) ? 0.f : -(ye[i] - yo[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vd[i] = vm[i] = 0.f;
+        }
+        float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + r) * a.pitch;
+        // direct half: lanes l and l ^ 4 hold neighbouring segments of one row; they swap half a segment
+        // so that each 16-byte store of the pair completes a 32-byte sector
+        {
+            const bool fast = active && a.vec_ok && (t0 + 7 <= nh);
+            const int partner_fast = __shfl_xor_sync(0xffffffffu, (int)fast, 4);
+            const bool pair = fast && partner_fast;
+            const bool odd = (lane >> 2) & 1;
+            float rcv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rcv[k] = __shfl_xor_sync(0xffffffffu, odd ? vd[k] : vd[4 + k], 4);
+            if (pair) {
+                float4 q1, q2;
+                if (!odd) {
+                    q1 = make_float4(vd[0], vd[1], vd[2], vd[3]);
+                    q2 = make_float4(rcv[0], rcv[1], rcv[2], rcv[3]);
+                } else {
+                    q1 = make_float4(rcv[0], rcv[1], rcv[2], rcv[3]);
+                    q2 = make_float4(vd[4], vd[5], vd[6], vd[7]);
                 }
+                float* p1 = orow + (odd ? t0 - 4 : t0);      // even: own 0..3          odd: partner's 4..7
+                float* p2 = orow + (odd ? t0 + 4 : t0 + 8);  // even: partner's 0..3    odd: own 4..7
+                *reinterpret_cast<float4*>(p1) = q1;
+                *reinterpret_cast<float4*>(p2) = q2;
+            } else if (active) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (t0 + i <= nh) orow[t0 + i] = vd[i];
+            }
+        }
+        // mirrored half: row by row through a 64-float staging line, written out as 2 x 128 contiguous bytes
+        {
+            const int s = lane >> 2;
+            const int tm_lo = n - (w0 / FR_ROWS) * 8 - 63;  // lowest address of the warp's 8 segments
+#pragma unroll
+            for (int rr = 0; rr < FR_ROWS; ++rr) {
+                if (active && r == rr) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) stage[8 * (7 - s) + (7 - i)] = vm[i];
+                }
+                __syncwarp();
+                if (rr < nrows) {
+                    float* orr = a.cH + (size_t)z * a.pstride + (size_t)(row0 + rr) * a.pitch;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int p = lane + 32 * h;
+                        const int tm = tm_lo + p;
+                        // n - tm = t in 1..nh with tm != t, inside the segments that exist
+                        if (tm > nh && tm < n) orr[tm] = stage[p];
+                    }
+                }
+                __syncwarp();
             }
         }
     }
