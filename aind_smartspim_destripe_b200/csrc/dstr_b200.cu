@@ -95,6 +95,7 @@ struct dstr_ctx {
     bool use_tma = true;  // level-1 analysis through the TMA-staged kernel when the plane shape allows
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     float fg_half_thr = 384.f;
+    float fg_thr32 = 384.f;  // the same rule on the float32 value (fg_threshold_f32)
     double notch_eps = 1e-6;  // truncation tolerance of the hybrid notch operator (0 = dense)
     // instrumentation
     bool profiling = false;
@@ -160,6 +161,34 @@ float find_fg_half_threshold(float threshold_mask) {
         if (fg_rule(half_from_bits(bits), thr)) return half_from_bits(bits);
     }
     return INFINITY;
+}
+
+// The device applies the rule to the float32 pixel value directly: float16 rounding is monotone,
+// so "float16(v) >= h" is "v >= t" for the smallest float32 t that rounds to a float16 >= h
+// (found by bisection over the ordered float32 bit patterns).  NaN encodes "never".
+float fg_threshold_f32(float half_thr) {
+    if (std::isinf(half_thr)) return half_thr < 0.f ? -INFINITY : NAN;
+    auto key = [](float f) {
+        uint32_t b;
+        std::memcpy(&b, &f, 4);
+        return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    };
+    auto unkey = [](uint32_t k) {
+        const uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+        float f;
+        std::memcpy(&f, &b, 4);
+        return f;
+    };
+    uint32_t hi = key(half_thr);  // satisfies the rule
+    uint32_t lo = key(-INFINITY); // float16(-inf) = -inf < half_thr
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (half_round(unkey(mid)) >= half_thr)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return unkey(hi);
 }
 
 // ---- time-domain form of the packed-rfft notch (filtering.py:206-215, scipy.fftpack layout) --
@@ -512,7 +541,7 @@ int launch_analysis(const Pass& P, int l, cudaStream_t st) {
 #define LAUNCH_AN1(IN_T, ST, VEC)                                                                       \
     analysis_kernel<IN_T, true, ST, VEC><<<grid, AN_THREADS, 0, st>>>(                                   \
         (const IN_T*)P.d_in, H, W, W, (size_t)H * W, ctx->d_A[1], ctx->d_H[1], go.H, go.W, go.pitch,     \
-        go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_half_thr)
+        go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_thr32)
 #define LAUNCH_AN1V(IN_T, ST)                \
     do {                                     \
         if (vec) LAUNCH_AN1(IN_T, ST, true); \
@@ -528,7 +557,7 @@ int launch_analysis(const Pass& P, int l, cudaStream_t st) {
 #define LAUNCH_TMA(IN_T, ST)                                                                              \
     analysis_tma_kernel<IN_T, ST><<<gt, AT_THREADS, 0, st>>>((const IN_T*)P.d_in, H, W, (size_t)H * W, ctx->d_A[1], \
                                                               ctx->d_H[1], go.H, go.W, go.pitch, go.pstride, ls,  \
-                                                              P.stat_stride, ctx->d_pstat, ctx->fg_half_thr, rows_per_cta)
+                                                              P.stat_stride, ctx->d_pstat, ctx->fg_thr32, rows_per_cta)
         if (P.in_dtype == DSTR_U16) {
             if (stats) LAUNCH_TMA(uint16_t, true);
             else LAUNCH_TMA(uint16_t, false);
@@ -548,11 +577,11 @@ int launch_analysis(const Pass& P, int l, cudaStream_t st) {
     } else if (vec) {
         analysis_kernel<float, false, false, true><<<grid, AN_THREADS, 0, st>>>(
             ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H, go.W, go.pitch,
-            go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+            go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_thr32);
     } else {
         analysis_kernel<float, false, false, false><<<grid, AN_THREADS, 0, st>>>(
             ctx->d_A[l - 1], gs.H, gs.W, gs.pitch, gs.pstride, ctx->d_A[l], ctx->d_H[l], go.H, go.W, go.pitch,
-            go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_half_thr);
+            go.pstride, ls, P.stat_stride, ctx->d_pstat, ctx->fg_thr32);
     }
 #undef LAUNCH_AN1V
 #undef LAUNCH_AN1
@@ -898,6 +927,9 @@ int dstr_level_shape(int H, int W, int level, int* H_l, int* W_l) {
 }
 
 float dstr_foreground_threshold(float threshold_mask) { return find_fg_half_threshold(threshold_mask); }
+float dstr_foreground_threshold_f32(float threshold_mask) {
+    return fg_threshold_f32(find_fg_half_threshold(threshold_mask));
+}
 
 int dstr_notch_kernels(int n, double s, double* hp, double* hq) {
     if (n <= 0 || !(s > 0.0) || !hp || !hq) return DSTR_E_ARG;
@@ -971,6 +1003,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
     }
 #undef CKC
     ctx->fg_half_thr = find_fg_half_threshold(0.3f);
+    ctx->fg_thr32 = fg_threshold_f32(ctx->fg_half_thr);
     ctx->subchunk = 0;
     *out = ctx;
     return 0;
@@ -1214,7 +1247,7 @@ int dstr_plane_stats(dstr_ctx* ctx, const void* in, int in_dtype, int Z, double*
         if (rc) return rc;
     }
     std::vector<PlaneStat> hs(sub);
-    const float fg_thr = (threshold_mask == 0.3f) ? ctx->fg_half_thr : find_fg_half_threshold(threshold_mask);
+    const float fg_thr = (threshold_mask == 0.3f) ? ctx->fg_thr32 : fg_threshold_f32(find_fg_half_threshold(threshold_mask));
     for (int z0 = 0; z0 < Z; z0 += sub) {
         const int zn = std::min(sub, Z - z0);
         const void* src = (const char*)in + (size_t)z0 * in_pb;

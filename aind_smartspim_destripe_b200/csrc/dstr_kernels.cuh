@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(AN_THREADS, DSTR_AN_MINB)
 analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_t in_pstride,
                 float* __restrict__ cA, float* __restrict__ cH, int Ho, int Wo, int out_pitch,
                 size_t out_pstride, LevelStat* __restrict__ lstat, int stat_stride,
-                PlaneStat* __restrict__ pstat, float fg_half_thr) {
+                PlaneStat* __restrict__ pstat, float fg_thr32) {
     __shared__ float s_red[2][AN_WARPS];
     __shared__ double s_dred[2][AN_WARPS];
     __shared__ unsigned s_cred[2][AN_WARPS];
@@ -305,8 +305,8 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
                 if (STATS) {
                     const int gy0 = 2 * oy0 - 4 + r;
                     if (r >= 4 && gy0 < Hs) {  // rows owned by this tile: [2 oy0, 2 oy0 + 2 AN_TOY)
-                        const bool f0 = own0 && (__half2float(__float2half_rn(v0)) >= fg_half_thr);
-                        const bool f1 = own1 && (__half2float(__float2half_rn(v1)) >= fg_half_thr);
+                        const bool f0 = own0 && (v0 >= fg_thr32);
+                        const bool f1 = own1 && (v1 >= fg_thr32);
                         all_s += own0 ? v0 : 0.f;
                         all_s += own1 ? v1 : 0.f;
                         all_c += (own0 ? 1u : 0u) + (own1 ? 1u : 0u);
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(AT_THREADS)
 analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstride, float* __restrict__ cA,
                     float* __restrict__ cH, int Ho, int Wo, int out_pitch, size_t out_pstride,
                     LevelStat* __restrict__ lstat, int stat_stride, PlaneStat* __restrict__ pstat,
-                    float fg_half_thr, int rows_per_cta) {
+                    float fg_thr32, int rows_per_cta) {
     __shared__ __align__(128) IN_T s_ring[AT_STAGES][AT_RS][AT_WIN];
     __shared__ __align__(8) uint64_t s_full[AT_STAGES];
     __shared__ float s_red[2][AT_WARPS];
@@ -536,8 +536,8 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
                 if (STATS) {
                     const int gy0 = 2 * oy0 - 4 + r;
                     if (r >= 4 && r < 4 + 2 * R && gy0 < Hs) {  // rows owned by this CTA
-                        const bool f0 = own0 && (__half2float(__float2half_rn(v0)) >= fg_half_thr);
-                        const bool f1 = own1 && (__half2float(__float2half_rn(v1)) >= fg_half_thr);
+                        const bool f0 = own0 && (v0 >= fg_thr32);
+                        const bool f1 = own1 && (v1 >= fg_thr32);
                         all_s += own0 ? v0 : 0.f;
                         all_s += own1 ? v1 : 0.f;
                         all_c += (own0 ? 1u : 0u) + (own1 ? 1u : 0u);
@@ -642,7 +642,7 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
 template <typename IN_T>
 __global__ void __launch_bounds__(256)
 plane_stats_kernel(const IN_T* __restrict__ in, int H, int W, size_t pstride,
-                   PlaneStat* __restrict__ pstat, float fg_half_thr) {
+                   PlaneStat* __restrict__ pstat, float fg_thr32) {
     __shared__ double s_dred[2][8];
     __shared__ unsigned s_cred[2][8];
     const int z = blockIdx.y;
@@ -652,8 +652,7 @@ plane_stats_kernel(const IN_T* __restrict__ in, int H, int W, size_t pstride,
     unsigned fg_c = 0, bg_c = 0;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         const float v = to_f32(src[i]);
-        const float hv = __half2float(__float2half_rn(v));
-        if (hv >= fg_half_thr) {
+        if (v >= fg_thr32) {
             fg_s += (double)v;
             fg_c++;
         } else {
@@ -728,23 +727,6 @@ __device__ __forceinline__ int hist_bin(float v, float first, float inv_width, c
     return idx;
 }
 
-// Warp-level accumulation tuned for the extremely skewed distribution of cH^2 (most samples in
-// the first bins): the four bins of every lane are first compared with one reference bin (that of
-// the first active lane); the matches of the whole warp are counted with a single warp reduction
-// and one shared-memory atomic, only the rest use individual atomics.
-__device__ __forceinline__ void hist_add4(unsigned* s_hist, int i0, int i1, int i2, int i3, int lane) {
-    const unsigned act = __ballot_sync(0xffffffffu, i0 >= 0);  // i0 < 0 <=> the whole quad is out of range
-    if (act == 0) return;
-    const int b0 = __shfl_sync(0xffffffffu, i0, __ffs(act) - 1);
-    const int same = (i0 == b0) + (i1 == b0) + (i2 == b0) + (i3 == b0);
-    const int total = __reduce_add_sync(0xffffffffu, same);
-    if (lane == 0) atomicAdd(&s_hist[b0], (unsigned)total);
-    if (i0 >= 0 && i0 != b0) atomicAdd(&s_hist[i0], 1u);
-    if (i1 >= 0 && i1 != b0) atomicAdd(&s_hist[i1], 1u);
-    if (i2 >= 0 && i2 != b0) atomicAdd(&s_hist[i2], 1u);
-    if (i3 >= 0 && i3 != b0) atomicAdd(&s_hist[i3], 1u);
-}
-
 __global__ void __launch_bounds__(256)
 hist_kernel(const float* __restrict__ cH, int Hl, int Wl, int pitch, size_t pstride,
             LevelStat* __restrict__ lstat, int stat_stride) {
@@ -765,23 +747,40 @@ hist_kernel(const float* __restrict__ cH, int Hl, int Wl, int pitch, size_t pstr
     const float inv_width = 256.0f / delta;
     const float* src = cH + (size_t)z * pstride;
     const int lane = tid & 31;
+    // cH^2 is extremely skewed: nearly every sample lies below the second edge.  Those are counted in a
+    // register (bin 0 <=> q < edges[1], the same float32 comparison the fix-up of np.histogram ends
+    // on); only the rest goes through the general bin search and the shared-memory atomics.
+    const float e1 = s_edges[1];
+    unsigned cnt0 = 0;
     // the band is walked as float4 quads over the padded rows (pitch % 4 == 0, 16-byte aligned)
     const int qpr = pitch >> 2;  // quads per row
     const int nquads = Hl * qpr;
-    const int nq_up = (nquads + 255) & ~255;
-    for (int qi = blockIdx.x * 256 + tid; qi < nq_up; qi += gridDim.x * 256) {
-        int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
-        if (qi < nquads) {
-            const int r = qi / qpr;
-            const int c = (qi - r * qpr) << 2;
-            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * pitch + c);
-            if (c < Wl) i0 = hist_bin(v.x, first, inv_width, s_edges);
-            if (c + 1 < Wl) i1 = hist_bin(v.y, first, inv_width, s_edges);
-            if (c + 2 < Wl) i2 = hist_bin(v.z, first, inv_width, s_edges);
-            if (c + 3 < Wl) i3 = hist_bin(v.w, first, inv_width, s_edges);
+    // (row, quad) advance by a fixed (dr, dq) per step: one division per thread instead of one per quad
+    const int stride = gridDim.x * 256;
+    const int dr = stride / qpr, dq = stride - dr * qpr;
+    int r = (blockIdx.x * 256 + tid) / qpr;
+    int cq = (blockIdx.x * 256 + tid) - r * qpr;
+    for (int qi = blockIdx.x * 256 + tid; qi < nquads; qi += stride, r += dr, cq += dq) {
+        if (cq >= qpr) {
+            cq -= qpr;
+            ++r;
         }
-        hist_add4(s_hist, i0, i1, i2, i3, lane);
+        const int c = cq << 2;
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * pitch + c);
+        const float q[4] = {__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)};
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c + k < Wl) {
+                if (q[k] < e1)
+                    ++cnt0;
+                else
+                    atomicAdd(&s_hist[hist_bin(vv[k], first, inv_width, s_edges)], 1u);
+            }
+        }
     }
+    cnt0 = __reduce_add_sync(0xffffffffu, cnt0);
+    if (lane == 0 && cnt0) atomicAdd(&s_hist[0], cnt0);
     __syncthreads();
     const unsigned h = s_hist[tid];
     if (h) atomicAdd(&st->hist[tid], h);

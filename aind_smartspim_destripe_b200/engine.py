@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
             "dstr_max_level": (C.c_int, [C.c_int, C.c_int]),
             "dstr_level_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
             "dstr_foreground_threshold": (C.c_float, [C.c_float]),
+            "dstr_foreground_threshold_f32": (C.c_float, [C.c_float]),
             "dstr_notch_kernels": (C.c_int, [C.c_int, C.c_double, dp, dp]),
             "dstr_notch_design": (C.c_int, [C.c_int, C.c_double, C.c_double, ip]),
             "dstr_notch_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp]),
@@ -119,7 +120,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "dstr_create dstr_destroy dstr_last_error dstr_set_flat_dark dstr_filter_chunk dstr_plane_stats "
-    "dstr_flatfield_correction dstr_max_level dstr_level_shape dstr_foreground_threshold "
+    "dstr_flatfield_correction dstr_max_level dstr_level_shape dstr_foreground_threshold dstr_foreground_threshold_f32 "
     "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
@@ -183,6 +184,11 @@ def notch_apply_host(x: np.ndarray, s: float, eps: float = 1e-6) -> np.ndarray:
 
 def foreground_threshold(threshold_mask: float = 0.3) -> float:
     return float(load_library().dstr_foreground_threshold(float(threshold_mask)))
+
+
+def foreground_threshold_f32(threshold_mask: float = 0.3) -> float:
+    """The float16 rule as a threshold on the float32 pixel value (NaN = never)."""
+    return float(load_library().dstr_foreground_threshold_f32(float(threshold_mask)))
 
 
 def make_params(cfg: Optional[dict]) -> Optional[DstrParams]:

@@ -128,6 +128,10 @@ int dstr_level_shape(int H, int W, int level, int* H_l, int* W_l);
  * arithmetic, i.e. the foreground rule of get_foreground_background_mean (filtering.py:78-81)
  * as a threshold on float16(pixel); -inf / +inf when the rule holds everywhere / nowhere. */
 float dstr_foreground_threshold(float threshold_mask);
+/* The same rule as a threshold on the float32 pixel value (what the kernels compare against):
+ * float16 rounding is monotone, so float16(v) >= h  <=>  v >= t for the smallest float32 t whose
+ * float16 rounding is >= h.  -inf when the rule holds everywhere, NaN when it holds nowhere. */
+float dstr_foreground_threshold_f32(float threshold_mask);
 /* Time-domain form of the reference's packed-rfft notch (filtering.py:206-215):
  * irfft(rfft(x) * g) = x - B x with B[t][v] = hp[(t - v) mod n] + hq[(t + v) mod n].
  * Writes n doubles to each of hp, hq. */

@@ -93,6 +93,22 @@ def test_foreground_threshold_matches_float16_rule():
     assert E.foreground_threshold(1.0) == np.inf
 
 
+def test_float32_foreground_threshold_equals_the_float16_rule():
+    # the kernels compare the float32 pixel with dstr_foreground_threshold_f32 instead of rounding to float16
+    rng = np.random.default_rng(5)
+    for tm in [0.3, 0.0, 0.05, 0.5, 0.7, 0.95]:  # 0.0: the float16 sigmoid underflows below ~178
+        h = np.float32(E.foreground_threshold(tm))
+        t = np.float32(E.foreground_threshold_f32(tm))
+        v = np.concatenate([np.arange(65536, dtype=np.float32),
+                            (h + rng.uniform(-2, 2, 20000)).astype(np.float32),
+                            np.nextafter(t, np.float32(-np.inf), dtype=np.float32)[None], t[None],
+                            np.float32([-1e6, 1e6, np.inf, -np.inf, np.nan])])
+        with np.errstate(over="ignore", invalid="ignore"):
+            rule = v.astype(np.float16).astype(np.float32) >= h
+            np.testing.assert_array_equal(rule, v >= t)
+    assert np.isnan(E.foreground_threshold_f32(1.0))  # never foreground
+
+
 def test_make_params_validation():
     p = E.make_params({"wavelet": "db3", "level": None, "sigma": 128, "max_threshold": 12})
     assert p.level == -1 and p.sigma == 128.0 and p.max_threshold == 12.0
