@@ -297,3 +297,257 @@ def destripe_volume(
         raise errors[0]
     times["planes"] = z1 - z0
     return times
+
+
+# ----------------------------------------------------------------------------------------------
+# Tile driver (SURVEY.md §8 "next" row f1): destripe_zarr / destripe_channel of the reference
+# (zarr_destriper.py:909-1267) on destripe_volume.  Zarr I/O goes through ``zarr_store`` (the
+# ``zarr`` package when importable); TIFF flats / darks through ``destriper.imread``.
+# ----------------------------------------------------------------------------------------------
+def get_microscope_flats(channel_name: str, derivatives_folder):
+    """Per-hemisphere microscope flats + the X/Y-folder -> side map from ``metadata.json``
+    (reference zarr_destriper.py:70-153).  Returns ``(flatfields | None, tile_config | None)``."""
+    import json
+    import re
+    from pathlib import Path
+
+    from .destriper import imread
+
+    derivatives_folder = Path(derivatives_folder)
+    waves = [p for p in str(channel_name).split("_") if p.isdigit()]
+    metadata_path = derivatives_folder / "metadata.json"
+    if not (metadata_path.exists() and waves):
+        return None, None
+    with open(metadata_path) as fp:
+        tile_config = json.load(fp).get("tile_config")
+    if tile_config is None:
+        raise ValueError("Please, verify metadata.json")
+    wave = int(waves[0])
+    sides: dict = {}
+    for entry in tile_config.values():
+        if int(entry.get("Laser")) != wave:
+            continue
+        x_folder, y_folder, side = entry.get("X"), entry.get("Y"), entry.get("Side")
+        if x_folder is None or y_folder is None or side is None:
+            raise KeyError("Please, check the data in metadata.json")
+        sides.setdefault(x_folder, {})[y_folder] = int(side)
+
+    def natural(p):
+        return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", p.name)]
+
+    flats = [np.asarray(imread(p)) for p in sorted(derivatives_folder.glob(f"FlatReal{wave}_*.tif"), key=natural)]
+    if len(flats) != 2:
+        raise ValueError(f"Error while reading the microscope flatfields: found {len(flats)}, expected 2")
+    return flats, sides
+
+
+def _compute_scales(scale_num_levels, scale_factor, pixelsizes, chunks, data_shape):
+    """coordinateTransformations + chunk shapes per level (reference :410-500)."""
+    scale = [1.0, 1.0, float(pixelsizes[0]), float(pixelsizes[1]), float(pixelsizes[2])]
+    z, y, x = data_shape[2:]
+    transforms, chunk_sizes = [], []
+    for lvl in range(scale_num_levels):
+        if lvl:
+            scale = scale[:2] + [scale[2 + i] * scale_factor[i] for i in range(3)]
+            z, y, x = (int(np.ceil(v / f)) for v, f in zip((z, y, x), scale_factor))
+        transforms.append([{"type": "scale", "scale": list(scale)}])
+        chunk_sizes.append((1, 1, min(z, chunks[2]), min(y, chunks[3]), min(x, chunks[4])))
+    return transforms, chunk_sizes
+
+
+def _build_ome(data_shape, image_name, channel_colors, channel_minmax, channel_startend):
+    """``omero`` block (reference :531-597)."""
+    channels = []
+    for i in range(data_shape[1]):
+        channels.append({
+            "active": True, "coefficient": 1, "color": f"{channel_colors[i]:06x}", "family": "linear",
+            "inverted": False, "label": image_name,
+            "window": {"end": float(channel_startend[i][1]), "max": float(channel_minmax[i][1]),
+                       "min": float(channel_minmax[i][0]), "start": float(channel_startend[i][0])},
+        })
+    return {"id": 1, "name": image_name, "version": "0.4", "channels": channels,
+            "rdefs": {"defaultT": 0, "defaultZ": data_shape[2] // 2, "model": "color"}}
+
+
+def ome_ngff_metadata(data_shape, chunks, image_name, n_lvls, scale_factors, voxel_size) -> dict:
+    """The ``.zattrs`` the reference writes next to the levels (OME-NGFF 0.4: ``multiscales`` with
+    one scale transform per level, ``omero`` display block; reference :600-674 and :703-727)."""
+    transforms, _ = _compute_scales(n_lvls, scale_factors, voxel_size, chunks, data_shape)
+    axes = [
+        {"name": "t", "type": "time", "unit": "millisecond"},
+        {"name": "c", "type": "channel"},
+        {"name": "z", "type": "space", "unit": "micrometer"},
+        {"name": "y", "type": "space", "unit": "micrometer"},
+        {"name": "x", "type": "space", "unit": "micrometer"},
+    ]
+    datasets = [{"path": str(i), "coordinateTransformations": transforms[i]} for i in range(n_lvls)]
+    n_c = data_shape[1]
+    info = np.iinfo(np.uint16)
+    return {
+        "omero": _build_ome(data_shape, image_name, [0x690AFE] * n_c, [(info.min, info.max)] * n_c,
+                            [(0.0, 350.0)] * n_c),
+        "multiscales": [{"version": "0.4", "axes": axes, "datasets": datasets}],
+    }
+
+
+class _PlanesView:
+    """(Z, H, W) view of one (t, c) of a 5-D TCZYX array; Z-range indexing only."""
+
+    def __init__(self, arr, t: int = 0, c: int = 0):
+        self.arr, self.t, self.c = arr, t, c
+        self.shape = tuple(arr.shape[2:])
+        self.dtype = np.dtype(arr.dtype)
+
+    def __getitem__(self, key):
+        return np.asarray(self.arr[self.t, self.c, key])
+
+    def __setitem__(self, key, value):
+        self.arr[self.t, self.c, key] = value
+
+
+def destripe_zarr(
+    dataset_path,
+    multiscale: str,
+    output_destriped_zarr,
+    prediction_chunksize: Tuple[int, ...],
+    target_size_mb: int,
+    n_workers: int,
+    batch_size: int,
+    super_chunksize: Optional[Tuple[int, ...]],
+    results_folder,
+    derivatives_path,
+    xyz_resolution,
+    parameters: dict,
+    flatfield=None,
+    lazy_callback_fn=None,
+    n_levels: int = 3,
+    compressor="default",
+    rank: Optional[int] = None,
+    world_size: Optional[int] = None,
+):
+    """Destripe one tile ``<dataset_path>/<multiscale>`` (TCZYX) into ``<output_destriped_zarr>/0``
+    and write the 2x multiscale levels + OME-NGFF metadata (reference zarr_destriper.py:909-1211).
+
+    Same arguments as the reference.  ``target_size_mb``, ``batch_size`` and ``super_chunksize``
+    described its DataLoader and are accepted and ignored: chunks of ``prediction_chunksize[0]``
+    planes stream through pinned buffers instead.  ``n_workers`` is the number of chunk
+    decode / encode threads (0 = 8).  With ``world_size`` > 1 (default: ``WORLD_SIZE`` / ``RANK`` of
+    a torchrun launch) every rank processes its own Z-slab; there is no collective.
+    """
+    import os
+    from pathlib import Path
+
+    from . import zarr_store as zs
+    from .destriper import imread
+    from .distributed import env_rank
+
+    if lazy_callback_fn is not None:
+        raise NotImplementedError("lazy_callback_fn is not supported by the GPU tile driver")
+    no_cells_config, cells_config = parameters["no_cells_config"], parameters["cells_config"]
+    from_env = rank is None or world_size is None  # explicit rank / world_size: the caller runs rank 0 first
+    if from_env:
+        rank, world_size, _ = env_rank()
+    threads = int(n_workers) if n_workers and n_workers > 0 else 8
+    output_destriped_zarr = Path(output_destriped_zarr)
+    dataset_name = output_destriped_zarr.name
+
+    src = zs.open_array(Path(dataset_path) / str(multiscale), "r", threads)
+    if len(src.shape) != 5:
+        raise ValueError(f"expected a TCZYX array, got shape {src.shape}")
+    T, C, Z, H, W = src.shape
+
+    # dark / flat exactly as the reference resolves them (:1106-1138)
+    darkfield, tile_config = None, None
+    retrospective = flatfield is not None
+    derivatives_path = Path(derivatives_path)
+    if derivatives_path.exists():
+        dark_path = derivatives_path / "DarkMaster_cropped.tif"
+        if not dark_path.exists():
+            raise FileNotFoundError(f"Please, provide the current dark from the microscope! Provided path: {dark_path}")
+        darkfield = np.asarray(imread(dark_path))
+        if flatfield is None:
+            flatfield, tile_config = get_microscope_flats(output_destriped_zarr.parent.name, derivatives_path)
+            if flatfield is not None:
+                flatfield = fl.normalize_image(flatfield)
+    shadow = None
+    if flatfield is not None:
+        if darkfield is None:
+            raise FileNotFoundError(f"a flat field needs the microscope dark: {derivatives_path} does not exist")
+        shadow = {"retrospective": retrospective, "flatfield": flatfield, "darkfield": darkfield,
+                  "tile_config": tile_config}
+
+    chunk_planes = int(prediction_chunksize[-3])
+    out_chunks = (1, 1, 64, 128, 128)
+    fused = shadow is not None and n_levels in (2, 3) and chunk_planes % 4 == 0
+    shapes = [(T, C, Z >> k, H >> k, W >> k) for k in range(n_levels)]
+    # slab boundaries: no two ranks inside one stored chunk of any level (a chunk of level k spans
+    # min(64, Z >> k) << k planes of level 0), and whole streaming chunks
+    align = chunk_planes
+    for k in range(n_levels):
+        align = int(np.lcm(align, max(1, min(out_chunks[2], shapes[k][2])) << k))
+    if rank == 0:
+        zs.create_group(output_destriped_zarr, overwrite=True)
+        for k in range(n_levels):
+            zs.ZarrArray.create(output_destriped_zarr / str(k), shapes[k], out_chunks, np.uint16, compressor, "/")
+        voxel = [xyz_resolution[-1], xyz_resolution[-2], xyz_resolution[-3]]
+        zs.write_attrs(output_destriped_zarr,
+                       ome_ngff_metadata(shapes[0], out_chunks, dataset_name, n_levels, [2, 2, 2], voxel))
+    if world_size > 1 and from_env:
+        from . import distributed as dist
+
+        dist.init()
+        dist.barrier()  # rank 0 has created the arrays
+    levels = [zs.ZarrArray.open(output_destriped_zarr / str(k), "w", threads) for k in range(n_levels)]
+    z0, z1 = z_slab(Z, rank, world_size, align)
+    totals = dict(read_s=0.0, device_s=0.0, write_s=0.0, wall_s=0.0, planes=0)
+    for t in range(T):
+        for c in range(C):
+            pyr = [_PlanesView(levels[k], t, c) for k in range(1, n_levels)] if fused else None
+            if z1 > z0:
+                tm = destripe_volume(_PlanesView(src, t, c), _PlanesView(levels[0], t, c), no_cells_config, cells_config,
+                                     shadow, dataset_name=dataset_name, chunk_planes=chunk_planes, z_range=(z0, z1),
+                                     pyramid_outputs=pyr, io_threads=1)
+                for k in totals:
+                    totals[k] += tm[k]
+            if not fused and n_levels > 1 and z1 > z0:
+                # float output (no shadow correction) or unusual chunking: levels from the written data
+                a0 = z0 - z0 % 4
+                prev = np.asarray(levels[0][t, c, a0:z1])
+                for k in range(1, n_levels):
+                    prev = compute_pyramid(prev, 2, [2, 2, 2])[-1]
+                    levels[k][t, c, (a0 >> k) : (a0 >> k) + prev.shape[0]] = prev[: max(0, shapes[k][2] - (a0 >> k))]
+    for lv in levels:
+        lv.close()
+    if hasattr(src, "close"):
+        src.close()
+    return totals
+
+
+def destripe_channel(zarr_dataset_path, derivatives_path, channel_name, results_folder, xyz_resolution,
+                     estimated_channel_flats, laser_tiles, parameters):
+    """Every ``*.zarr`` tile of a channel with the flat field of its laser side
+    (reference zarr_destriper.py:1214-1267)."""
+    from pathlib import Path
+
+    from .destriper import imread
+
+    channel_dataset = Path(zarr_dataset_path) / channel_name
+    destriped_data_folder = Path(results_folder) / "destriped_data"
+    destriped_data_folder.mkdir(parents=True, exist_ok=True)
+    timings = {}
+    for tile_path in sorted(channel_dataset.glob("*.zarr")):
+        output_folder = destriped_data_folder / channel_name / tile_path.name
+        flatfield_path = None
+        for side, tiles in laser_tiles.items():
+            if tile_path.stem.rsplit(".", 1)[0] in tiles:
+                flatfield_path = estimated_channel_flats[int(side)]
+                break
+        if flatfield_path is None:
+            raise ValueError(f"Tile {tile_path} not found in {laser_tiles}")
+        flatfield = np.asarray(imread(str(flatfield_path)))
+        timings[tile_path.name] = destripe_zarr(
+            dataset_path=tile_path, multiscale="0", output_destriped_zarr=output_folder,
+            prediction_chunksize=(64, 1600, 2000), target_size_mb=3072, n_workers=0, batch_size=1,
+            super_chunksize=(384, 1600, 2000), results_folder=results_folder, derivatives_path=derivatives_path,
+            xyz_resolution=xyz_resolution, parameters=parameters, flatfield=flatfield, lazy_callback_fn=None)
+    return timings

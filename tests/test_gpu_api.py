@@ -238,3 +238,103 @@ def test_batch_filter_directory_matches_oracle(tmp_path, production_configs, wit
         assert out.dtype == np.uint16 and out.shape == img.shape
         frac, worst, _ = u16_agreement(out, ref)
         assert frac >= U16_FRACTION, (p.name, frac, worst)
+
+
+def _make_tile(path, vol):
+    from aind_smartspim_destripe_b200 import zarr_store as zs
+
+    zs.create_group(path)
+    arr = zs.ZarrArray.create(path / "0", (1, 1) + vol.shape, (1, 1, 32, 64, 64), np.uint16, {"id": "zlib", "level": 1})
+    arr[0, 0] = vol
+    arr.close()
+
+
+def test_destripe_zarr_tile_driver_matches_oracle(tmp_path, production_configs):
+    # /root/reference/code/aind_smartspim_destripe/zarr_destriper.py:909-1211 (tile -> destriped zarr + pyramid)
+    import json
+
+    from aind_smartspim_destripe_b200 import destriper as D
+    from aind_smartspim_destripe_b200 import zarr_store as zs
+    from oracle import pyramid as OP
+
+    no_cells, cells = production_configs
+    Z, H, W = 72, 160, 192
+    vol = S.synthetic_stack(Z, H, W, base_seed=77, cells_every=3, n_unique=6)
+    tile = tmp_path / "SPIM.ome.zarr" / "Ex_488_Em_525" / "471320_304840.zarr"
+    tile.parent.mkdir(parents=True)
+    _make_tile(tile, vol)
+    shadow = _shadow(H, W)
+    deriv = tmp_path / "derivatives"
+    deriv.mkdir()
+    D._tiff_write(str(deriv / "DarkMaster_cropped.tif"), shadow["darkfield"])
+    out = tmp_path / "results" / "Ex_488_Em_525" / tile.name
+    params = {"no_cells_config": no_cells, "cells_config": cells}
+    t = zd.destripe_zarr(tile, "0", out, (16, H, W), 3072, 0, 1, None, tmp_path, deriv, [1.8, 1.8, 2.0], params,
+                         flatfield=shadow["flatfield"], compressor={"id": "zlib", "level": 1})
+    assert t["planes"] == Z
+    lv = [zs.ZarrArray.open(out / str(k)) for k in range(3)]
+    assert lv[0].shape == (1, 1, Z, H, W) and lv[0].chunks == (1, 1, 64, 128, 128) and lv[0].dtype == np.uint16
+    assert lv[1].shape == (1, 1, Z // 2, H // 2, W // 2) and lv[2].shape == (1, 1, Z // 4, H // 4, W // 4)
+    got = lv[0][0, 0]
+    for z in range(0, Z, 7):
+        ref = OF.filter_stripes(vol[z].astype(np.float32), tile.name, no_cells, cells, shadow, 2500)
+        frac, worst, _ = u16_agreement(got[z], ref)
+        assert frac >= U16_FRACTION, (z, frac, worst)
+    # the multiscale levels are the truncating 2x2x2 means of the written level 0 (bit-exact)
+    pyr = OP.compute_pyramid(got, 3, [2, 2, 2])
+    np.testing.assert_array_equal(lv[1][0, 0], pyr[1])
+    np.testing.assert_array_equal(lv[2][0, 0], pyr[2])
+    attrs = json.loads((out / ".zattrs").read_text())
+    assert attrs["multiscales"][0]["datasets"][1]["coordinateTransformations"][0]["scale"] == [1.0, 1.0, 4.0, 3.6, 3.6]
+    assert json.loads((out / ".zgroup").read_text()) == {"zarr_format": 2}
+
+    # two "ranks" (run one after the other) write the same tile as one rank: slabs [0, 256) and [256, 320)
+    Z2, H2, W2 = 320, 96, 112
+    vol2 = S.synthetic_stack(Z2, H2, W2, base_seed=78, cells_every=5, n_unique=8)
+    tile2 = tile.parent / "471320_330760.zarr"
+    _make_tile(tile2, vol2)
+    sh2 = _shadow(H2, W2)
+    D._tiff_write(str(deriv / "DarkMaster_cropped.tif"), sh2["darkfield"])
+    outs = [tmp_path / f"results_w{w}" / "Ex_488_Em_525" / tile2.name for w in (1, 2)]
+    zd.destripe_zarr(tile2, "0", outs[0], (64, H2, W2), 3072, 2, 1, None, tmp_path, deriv, [1.8, 1.8, 2.0], params,
+                     flatfield=sh2["flatfield"], compressor=None, rank=0, world_size=1)
+    planes = [zd.destripe_zarr(tile2, "0", outs[1], (64, H2, W2), 3072, 2, 1, None, tmp_path, deriv, [1.8, 1.8, 2.0],
+                               params, flatfield=sh2["flatfield"], compressor=None, rank=r, world_size=2)["planes"]
+              for r in (0, 1)]
+    assert planes == [256, 64]
+    for k in range(3):
+        np.testing.assert_array_equal(zs.ZarrArray.open(outs[1] / str(k))[...], zs.ZarrArray.open(outs[0] / str(k))[...])
+
+
+def test_destripe_channel_picks_flat_by_laser_side(tmp_path, production_configs):
+    # /root/reference/code/aind_smartspim_destripe/zarr_destriper.py:1214-1267
+    from aind_smartspim_destripe_b200 import destriper as D
+    from aind_smartspim_destripe_b200 import zarr_store as zs
+
+    no_cells, cells = production_configs
+    Z, H, W = 1600 // 100, 96, 112  # destripe_channel fixes prediction_chunksize to (64, 1600, 2000): Z <= 64 here
+    vols = {name: S.synthetic_stack(Z, H, W, base_seed=s, n_unique=4) for name, s in [("100_200", 5), ("100_300", 9)]}
+    data = tmp_path / "SPIM.ome.zarr"
+    for name, vol in vols.items():
+        (data / "Ex_488_Em_525").mkdir(parents=True, exist_ok=True)
+        _make_tile(data / "Ex_488_Em_525" / f"{name}.zarr", vol)
+    sh = _shadow(H, W)
+    flats = [sh["flatfield"], (sh["flatfield"] * 1.25).astype(np.float32)]
+    deriv = tmp_path / "derivatives"
+    deriv.mkdir()
+    D._tiff_write(str(deriv / "DarkMaster_cropped.tif"), sh["darkfield"])
+    flat_paths = []
+    for i, f in enumerate(flats):
+        D._tiff_write(str(tmp_path / f"flat_{i}.tif"), f)
+        flat_paths.append(tmp_path / f"flat_{i}.tif")
+    params = {"no_cells_config": no_cells, "cells_config": cells}
+    zd.destripe_channel(data, deriv, "Ex_488_Em_525", tmp_path / "results", [1.8, 1.8, 2.0], flat_paths,
+                        {"0": ["100_200"], "1": ["100_300"]}, params)
+    for side, name in enumerate(["100_200", "100_300"]):
+        got = zs.ZarrArray.open(tmp_path / "results" / "destriped_data" / "Ex_488_Em_525" / f"{name}.zarr" / "0")[0, 0]
+        shadow = dict(retrospective=True, flatfield=flats[side], darkfield=sh["darkfield"], tile_config=None)
+        ref = fl.filter_planes(vols[name], name, no_cells, cells, shadow, 2500)
+        np.testing.assert_array_equal(got, ref)
+    with pytest.raises(ValueError):
+        zd.destripe_channel(data, deriv, "Ex_488_Em_525", tmp_path / "r2", [1.8, 1.8, 2.0], flat_paths,
+                            {"0": ["100_200"]}, params)
