@@ -477,6 +477,11 @@ def destripe_zarr(
                   "tile_config": tile_config}
 
     chunk_planes = int(prediction_chunksize[-3])
+    # stream whole source chunks when that stays small: a 128-deep source chunk read 64 planes at a
+    # time would be decoded twice
+    src_cz = int(getattr(src, "chunks", (1, 1, chunk_planes))[2])
+    if src_cz > chunk_planes and int(np.lcm(src_cz, chunk_planes)) <= 256:
+        chunk_planes = int(np.lcm(src_cz, chunk_planes))
     out_chunks = (1, 1, 64, 128, 128)
     fused = shadow is not None and n_levels in (2, 3) and chunk_planes % 4 == 0
     shapes = [(T, C, Z >> k, H >> k, W >> k) for k in range(n_levels)]
