@@ -328,6 +328,34 @@ def run_b200(args):
         e2e = {"value": world * px_per_step * args.steps / dt / 1e6, "unit": "Mpixel/s",
                "h2d_bytes_per_step": int(stack.nbytes), "d2h_bytes_per_step": int(stack.nbytes),
                "ms_per_step": 1e3 * dt / args.steps, "checksum": checksum}
+        # the ceiling of this figure: concurrent pinned H2D + D2H copies of the same buffers, nothing else
+        if rank == 0 and world == 1:
+            try:
+                t_in = torch.from_numpy(pin_in.array.reshape(-1).view(np.uint8))
+                t_out = torch.from_numpy(pin_out.array.reshape(-1).view(np.uint8))
+                g_in = torch.empty(t_in.numel(), dtype=torch.uint8, device=f"cuda:{device}")
+                g_out = torch.empty_like(g_in)
+                s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+                def both():
+                    with torch.cuda.stream(s1):
+                        g_in.copy_(t_in, non_blocking=True)
+                    with torch.cuda.stream(s2):
+                        t_out.copy_(g_out, non_blocking=True)
+
+                both()
+                torch.cuda.synchronize()
+                tc = time.perf_counter()
+                for _ in range(3):
+                    both()
+                torch.cuda.synchronize()
+                gbps = 3 * t_in.numel() / (time.perf_counter() - tc) / 1e9
+                e2e["pcie_bidirectional_GBps_each"] = gbps
+                e2e["pcie_ceiling_Mpixel_per_s"] = gbps * 1e9 / 2 / 1e6
+                e2e["frac_of_pcie_ceiling"] = e2e["value"] / e2e["pcie_ceiling_Mpixel_per_s"]
+                del g_in, g_out
+            except Exception as exc:  # the probe is informative only
+                e2e["pcie_probe_error"] = str(exc)
         pin_in.free()
         pin_out.free()
 
