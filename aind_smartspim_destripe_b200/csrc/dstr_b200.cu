@@ -243,6 +243,7 @@ void notch_kernels_host(int n, double s, std::vector<double>& hp, std::vector<do
 // to the L1 norm of the kernel (i.e. to the operator's gain on a bounded row).
 struct NotchHost {
     std::vector<float> te, to, T1, T2;
+    std::vector<float> T1f;  // T1 in mma A-fragment order for the device: [E block][Jpad / 16][lane][4]
     int ntap_e = 0, ue_lo = 0, ntap_o = 0, uo_lo = 0, J = 0, Jpad = 0;
 };
 
@@ -383,6 +384,7 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
         out.J = 0;
         out.Jpad = 0;
         out.T1.clear();
+        out.T1f.clear();
         out.T2.clear();
         return;
     }
@@ -407,6 +409,31 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
             out.T2[(size_t)j * nhp64 + off] = (float)(rho * c);
         }
     }
+    // Device copy of T1: the projection runs as m16n8k8 mma tiles over the 8-element blocks of the
+    // padded E row (logical index a = OFFe + v, block a >> 3).  Tile (block tb, modes 16 mt .. 16 mt + 15):
+    // lane (g = lane / 4, tig = lane % 4) holds a0 = (mode g, element tig), a1 = (mode g + 8, element
+    // tig), a2 = (mode g, element tig + 4), a3 = (mode g + 8, element tig + 4).
+    {
+        const int OFFe = out.ue_lo + out.ntap_e;
+        const int blk_lo = OFFe >> 3, blk_hi = (OFFe + nh + 1 + 7) >> 3;
+        const int nblk = blk_hi - blk_lo, mtiles = out.Jpad / 16;
+        out.T1f.assign((size_t)nblk * mtiles * 32 * 4, 0.f);
+        auto t1 = [&](int v, int j) -> float {
+            if (v < 0 || v > nh || j >= J) return 0.f;
+            return out.T1[(size_t)(v + 8) * out.Jpad + j];
+        };
+        for (int tb = 0; tb < nblk; ++tb)
+            for (int mt = 0; mt < mtiles; ++mt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, tig = lane & 3;
+                    const int v0 = 8 * (blk_lo + tb) - OFFe;
+                    float* dst = &out.T1f[(((size_t)tb * mtiles + mt) * 32 + lane) * 4];
+                    dst[0] = t1(v0 + tig, 16 * mt + g);
+                    dst[1] = t1(v0 + tig, 16 * mt + g + 8);
+                    dst[2] = t1(v0 + tig + 4, 16 * mt + g);
+                    dst[3] = t1(v0 + tig + 4, 16 * mt + g + 8);
+                }
+    }
 }
 
 int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
@@ -420,11 +447,11 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     design_notch(n, s, ctx->notch_eps, hst);
     auto pad32 = [](size_t v) { return (v + 31) & ~(size_t)31; };  // 128-byte aligned sub-tables
     const size_t o_te = 0, o_to = o_te + pad32(hst.te.size()), o_T1 = o_to + pad32(hst.to.size()),
-                 o_T2 = o_T1 + pad32(hst.T1.size()), total = o_T2 + pad32(hst.T2.size());
+                 o_T2 = o_T1 + pad32(hst.T1f.size()), total = o_T2 + pad32(hst.T2.size());
     std::vector<float> host(total, 0.f);
     std::copy(hst.te.begin(), hst.te.end(), host.begin() + o_te);
     std::copy(hst.to.begin(), hst.to.end(), host.begin() + o_to);
-    std::copy(hst.T1.begin(), hst.T1.end(), host.begin() + o_T1);
+    std::copy(hst.T1f.begin(), hst.T1f.end(), host.begin() + o_T1);
     std::copy(hst.T2.begin(), hst.T2.end(), host.begin() + o_T2);
     if (D.d_buf) {
         CK(ctx, cudaStreamSynchronize(ctx->s_comp));
@@ -436,7 +463,7 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     D.nt.te = D.d_buf + o_te;
     D.nt.to = D.d_buf + o_to;
-    D.nt.T1 = D.d_buf + o_T1 + (hst.J > 0 ? (size_t)8 * hst.Jpad : 0);  // points at the row of v = 0
+    D.nt.T1 = D.d_buf + o_T1;
     D.nt.T2 = D.d_buf + o_T2;
     D.nt.ntap_e = hst.ntap_e;
     D.nt.ue_lo = hst.ue_lo;
@@ -975,9 +1002,10 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         g.pitch = (g.W + 3) & ~3;
         g.pstride = (size_t)g.H * g.pitch;
         ctx->geom[l] = g;
-        // + 8 floats of slack: the synthesis kernel reads columns m+1, m+2 unconditionally
+        // slack: the synthesis kernel reads columns m+1, m+2 unconditionally (8 floats), the row filter
+        // loads whole 32-lane groups of a row (up to 31 floats past the last row)
         CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * (g.pstride * max_planes + 8)));
-        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 8)));
+        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 64)));
     }
     if (ctx->Lalloc > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lalloc * max_planes));
     CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));

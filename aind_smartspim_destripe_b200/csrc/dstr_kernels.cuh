@@ -918,32 +918,27 @@ __device__ __forceinline__ void fir8(float (&acc)[8], const float* __restrict__ 
     }
 }
 
-// Partial sums of c_j = sum_v T1[v][j] x_e[v] over the 8-element blocks [0, nblk) starting at eb / tt,
-// for all rows of the block at once (broadcast reads of x_e) and lanes j (and j + 32 when TWO).
-template <bool TWO, int ROWS>
-__device__ __forceinline__ void lr1_partial(const float* __restrict__ tt, const float* __restrict__ eb,
-                                            int row_stride, int nblk, int Jpad, float (&acc)[ROWS][2]) {
-    for (int blk = 0; blk < nblk; ++blk) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float t0 = __ldg(tt + i * Jpad);
-            const float t1 = TWO ? __ldg(tt + i * Jpad + 32) : 0.f;
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                const float xe = eb[r * row_stride + i];
-                acc[r][0] = fmaf(xe, t0, acc[r][0]);
-                if (TWO) acc[r][1] = fmaf(xe, t1, acc[r][1]);
-            }
-        }
-        tt += 8 * Jpad;
-        eb += 9;
-    }
+// ---- rank-J projection on the tensor path ----------------------------------------------------
+// c[j][r] = sum_v T1[v][j] x_e[r][v] is a (Jpad x nv) x (nv x rows) product: legacy
+// mma.sync m16n8k8 (HMMA.1688.F32.TF32; 278 TFLOP/s measured on this part, tools/probes) with the
+// 3xTF32 split a = a_hi + a_lo (a_hi = the 19 leading bits, a_lo = a - a_hi exactly):
+// a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo, i.e. float32-class products (the dropped a_lo b_lo term
+// is 2^-22 relative) accumulated in float32.
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 struct NotchTables {
     const float* te;  // even-part FIR taps [ntap_e]; tap k <-> circular offset u = ue_lo + k
     const float* to;  // odd-part FIR taps  [ntap_o]; tap k <-> u = uo_lo + k
-    const float* T1;  // [nhp4][Jpad]  omega_v cos(2 pi j v / n)   (v-major)
+    const float* T1;  // omega_v cos(2 pi j v / n) in mma A-fragment order: [E block][Jpad / 16][lane][4]
     const float* T2;  // [J][nhp64]    rho_j   cos(2 pi j t / n)   (j-major; inside a row the two float4
                       //               halves of 8 consecutive 8-output segments are grouped: see t2_offset)
     int ntap_e, ue_lo, ntap_o, uo_lo, J, Jpad;
@@ -968,7 +963,23 @@ struct FilterLevelArgs {
 };
 
 template <int EPL>
-__global__ void __launch_bounds__(FR_THREADS)
+// 8 blocks per SM (64 registers) for rows up to 33 x 32 elements; wider rows keep more keys in
+// registers and run 4 blocks per SM
+#ifndef DSTR_FR_MINB
+#define DSTR_FR_MINB 8
+#endif
+#ifndef DSTR_BUILD_UNROLL
+#define DSTR_BUILD_UNROLL 1
+#endif
+#ifndef DSTR_LR1_UNROLL
+#define DSTR_LR1_UNROLL 2
+#endif
+#ifndef DSTR_LR2_UNROLL
+#define DSTR_LR2_UNROLL 2
+#endif
+#define DSTR_PRAGMA(x) _Pragma(#x)
+#define DSTR_UNROLL(n) DSTR_PRAGMA(unroll n)
+__global__ void __launch_bounds__(FR_THREADS, (EPL <= 33 ? DSTR_FR_MINB : 4))
 filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.Wl;
@@ -1018,14 +1029,22 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     if (wid < nrows) {
         const float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
         // ---- load, mask, keys ------------------------------------------------------------
+        // every load of the row is issued before the first use (one memory round trip per row instead
+        // of one per few elements): unconditional loads at immediate offsets from one base; the lanes
+        // past the end of the row read into the next row / the slack behind the buffer and are discarded
         unsigned key[EPL];
+        {
+            const float* gl = grow + lane;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) key[i] = __float_as_uint(gl[32 * i]);
+        }
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
             const int e = lane + 32 * i;
+            const float c = __uint_as_float(key[i]);
             key[i] = 0xffffffffu;
             bool m = false;
             if (e < n) {
-                const float c = grow[e];
                 m = __fmul_rn(c, c) > thr_q;
                 key[i] = f2key(m ? 0.0f : (c + 0.0f));  // zero-filled background, canonical +0
             }
@@ -1111,6 +1130,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             int t = (tau_lo + lane) % n;
             if (t < 0) t += n;
             const int step = 32 % n;
+            DSTR_UNROLL(DSTR_BUILD_UNROLL)
             for (int tau = tau_lo + lane; tau < tau_hi && !(abl & 64); tau += 32) {
                 const int tr = (t == 0) ? 0 : n - t;
                 const float c1 = grow[t], c2 = grow[tr];
@@ -1128,9 +1148,10 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
 
     // ---- rank-J correction coefficients  c_j = sum_v T1[v][j] x_e[v], all rows at once ----------
     // x_e[v] sits at logical index v + OFFe of the padded E rows.  The index range is walked in the
-    // 8-element blocks of the padded layout (immediate offsets inside a block); warp w takes the
-    // w-th quarter of the blocks for all rows.  T1 carries 8 zero rows before v = 0 and after
-    // v = nh, so the partial first / last blocks need no predicates.
+    // 8-element blocks of the padded layout = the k-steps of the mma; warp w takes the w-th quarter
+    // of the blocks.  A = T1 (16 modes x 8 elements per tile, fragment-ordered on the host, zero
+    // outside 0 <= v <= nh and j < J so the partial first / last blocks need no predicates),
+    // B = x_e (8 elements x 8 columns; columns 0..3 = the rows of the block, 4..7 zero).
     if (nt.J > 0 && !(abl & 2)) {
         const int OFFe = nt.ue_lo + nt.ntap_e;
         const int Jpad = nt.Jpad;
@@ -1138,25 +1159,50 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
         const int blk_lo = OFFe >> 3, blk_hi = (OFFe + nv + 7) >> 3;
         const int bw = (blk_hi - blk_lo + FR_ROWS - 1) / FR_ROWS;
         const int b_begin = blk_lo + wid * bw, b_end = min(blk_hi, b_begin + bw);
-        for (int j0 = 0; j0 < Jpad; j0 += 64) {
-            const bool two = (j0 + 32) < Jpad;
-            float acc[FR_ROWS][2];
+        const int g = lane >> 2, tig = lane & 3;
+        const int mtiles = Jpad >> 4;
+        for (int j0 = 0; j0 < Jpad; j0 += 32) {  // two 16-mode tiles per pass
+            float acc[2][4];
 #pragma unroll
-            for (int r = 0; r < FR_ROWS; ++r) acc[r][0] = acc[r][1] = 0.f;
-            const float* tt = nt.T1 + (ptrdiff_t)(8 * b_begin - OFFe) * Jpad + j0 + lane;
-            const float* eb = s_E + 9 * b_begin;  // rows >= nrows: unused garbage
-            if (two)
-                lr1_partial<true, FR_ROWS>(tt, eb, a.xlen_e_phys, b_end - b_begin, Jpad, acc);
-            else
-                lr1_partial<false, FR_ROWS>(tt, eb, a.xlen_e_phys, b_end - b_begin, Jpad, acc);
+            for (int m = 0; m < 2; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+            const float4* tf = reinterpret_cast<const float4*>(nt.T1) +
+                               ((size_t)(b_begin - blk_lo) * mtiles + (j0 >> 4)) * 32 + lane;
+            const float* eb = s_E + (g & 3) * a.xlen_e_phys + 9 * b_begin + tig;  // rows >= nrows: unused garbage
+            DSTR_UNROLL(DSTR_LR1_UNROLL)
+            for (int blk = b_begin; blk < b_end; ++blk) {
+                const float x0 = (g < FR_ROWS) ? eb[0] : 0.f;
+                const float x1 = (g < FR_ROWS) ? eb[4] : 0.f;
+                unsigned bh0, bl0, bh1, bl1;
+                split_tf32(x0, bh0, bl0);
+                split_tf32(x1, bh1, bl1);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const float4 t = __ldg(tf + m * 32);
+                    unsigned ah[4], al[4];
+                    split_tf32(t.x, ah[0], al[0]);
+                    split_tf32(t.y, ah[1], al[1]);
+                    split_tf32(t.z, ah[2], al[2]);
+                    split_tf32(t.w, ah[3], al[3]);
+                    mma_tf32(acc[m], al, bh0, bh1);
+                    mma_tf32(acc[m], ah, bl0, bl1);
+                    mma_tf32(acc[m], ah, bh0, bh1);
+                }
+                tf += mtiles * 32;
+                eb += 9;
+            }
             // each warp holds the partial sums of its range of v: combine in shared memory as
             // 2^-32 fixed point (|c_j| < 2^30 by far; integer adds commute, so the result does
             // not depend on the order in which the warps arrive)
+            // accumulator fragment: acc[m][0..1] = mode 16 m + g, columns 2 tig, 2 tig + 1; acc[m][2..3] = mode + 8
+            if (tig < FR_ROWS / 2) {
 #pragma unroll
-            for (int r = 0; r < FR_ROWS; ++r) {
-                unsigned long long* pp = s_c64 + r * a.Jpad_max + j0 + lane;
-                atomicAdd(pp, (unsigned long long)__float2ll_rn(acc[r][0] * 4294967296.0f));
-                if (two) atomicAdd(pp + 32, (unsigned long long)__float2ll_rn(acc[r][1] * 4294967296.0f));
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = 2 * tig + (q & 1);
+                        const int j = j0 + 16 * m + g + ((q & 2) ? 8 : 0);
+                        atomicAdd(s_c64 + r * a.Jpad_max + j, (unsigned long long)__float2ll_rn(acc[m][q] * 4294967296.0f));
+                    }
             }
         }
         __syncthreads();
@@ -1190,7 +1236,7 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 // outputs 8 seg .. 8 seg + 3 at float4 index 16 (seg / 8) + seg % 8, the next four 8 further
                 const float4* t2 = reinterpret_cast<const float4*>(nt.T2) + 16 * (seg >> 3) + (seg & 7);
                 const int stride4 = a.nhp64 >> 2;
-#pragma unroll 4
+                DSTR_UNROLL(DSTR_LR2_UNROLL)
                 for (int j = 0; j < nt.J; ++j) {
                     const float c = cp[j];
                     const float4 u0 = __ldg(t2);
