@@ -1361,23 +1361,21 @@ struct EpilogueArgs {
 
 // VEC (FINAL only): Wo and the plane stride are even, so the two pixels of a lane are one aligned
 // word of the image, of the output and of the dark / flat fields.
-template <bool FINAL, typename IN_T, typename OUT_T, bool VEC>
-__global__ void __launch_bounds__(SY_THREADS, DSTR_SY_MINB)
-synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl, int Wl, int pitch_l,
+// One warp tile of the synthesis.  INTERIOR: every coefficient / pixel the tile touches lies inside the
+// band and the image, so all clamps and boundary predicates fold away (95 % of the tiles of a 2048^2 plane).
+template <bool FINAL, typename IN_T, typename OUT_T, bool VEC, bool INTERIOR>
+__device__ __forceinline__ void synth_tile(const float* __restrict__ dA, const float* __restrict__ dH, int Hl, int Wl, int pitch_l,
              size_t pstride_l, float* __restrict__ outA, int Ho, int Wo, int pitch_o,
              size_t pstride_o, const IN_T* __restrict__ img, OUT_T* __restrict__ out,
-             size_t img_pstride, EpilogueArgs ep) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+             size_t img_pstride, EpilogueArgs ep, int x0, int y0) {
+    const int lane = threadIdx.x & 31;
     const int z = blockIdx.z;
-    const int x0 = (blockIdx.x * SY_WARPS + wid) * SY_TX;
-    const int y0 = blockIdx.y * SY_TY;
-    if (x0 >= Wo) return;  // no block-level synchronisation below
     const int m = (x0 >> 1) + lane;
     const int cy0 = y0 >> 1;
     // clamped coefficient columns: out-of-range columns only feed discarded outputs or are
     // multiplied by the zero that replaces them below
-    const bool c0 = m < Wl, c1 = m + 1 < Wl, c2 = m + 2 < Wl;
-    const int mc = min(m, Wl - 1);
+    const bool c0 = INTERIOR || m < Wl, c1 = INTERIOR || m + 1 < Wl, c2 = INTERIOR || m + 2 < Wl;
+    const int mc = INTERIOR ? m : min(m, Wl - 1);
     const float* pA = dA ? dA + (size_t)z * pstride_l + mc : nullptr;
     const float* pH = dH ? dH + (size_t)z * pstride_l + mc : nullptr;
     const int o1 = c1 ? 1 : 0, o2 = c2 ? 2 : 0;
@@ -1388,7 +1386,7 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
     // unconditional on clamped addresses (the level buffers carry a few floats of slack), values
     // outside the band are replaced by zero afterwards, so the compiler can hoist every load.
     auto fetch = [&](int r, float (&c)[6]) {
-        const int gy = min(cy0 + r, Hl - 1);
+        const int gy = INTERIOR ? cy0 + r : min(cy0 + r, Hl - 1);
         const unsigned o = (unsigned)(gy * pitch_l);
         if (pA) {
             const float* q = pA + o;
@@ -1408,7 +1406,7 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
         }
     };
     auto xpass = [&](int r, const float (&c)[6], float& L0, float& L1, float& G0, float& G1) {
-        const bool rok = (cy0 + r) < Hl;
+        const bool rok = INTERIOR || (cy0 + r) < Hl;
         const float a0 = (rok && c0) ? c[0] : 0.f, a1 = (rok && c1) ? c[1] : 0.f, a2 = (rok && c2) ? c[2] : 0.f;
         const float h0 = (rok && c0) ? c[3] : 0.f, h1 = (rok && c1) ? c[4] : 0.f, h2 = (rok && c2) ? c[5] : 0.f;
         // x = 2m + px: sum_j rec_lo[2j + px] * c[m + 2 - j]
@@ -1430,11 +1428,11 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
         xpass(1, cb, L0[1], L1[1], G0[1], G1[1]);
     }
     const int gx = 2 * m;
-    const bool v0ok = gx < Wo, v1ok = gx + 1 < Wo;
+    const bool v0ok = INTERIOR || gx < Wo, v1ok = INTERIOR || gx + 1 < Wo;
     const float one = ep.expm1 ? -1.0f : 1.0f;
     typedef RawPair<IN_T, VEC> Raw;
-    const int gxc = min(gx, Wo - (VEC ? 2 : 1));  // clamped columns (loads only)
-    const int gx1c = min(gx + 1, Wo - 1);
+    const int gxc = INTERIOR ? gx : min(gx, Wo - (VEC ? 2 : 1));  // clamped columns (loads only)
+    const int gx1c = INTERIOR ? gx + 1 : min(gx + 1, Wo - 1);
     const IN_T* img_z = FINAL ? img + (size_t)z * img_pstride : nullptr;
     OUT_T* out_z = FINAL ? out + (size_t)z * img_pstride : nullptr;
     float* outA_z = FINAL ? nullptr : outA + (size_t)z * pstride_o + gx;
@@ -1456,7 +1454,7 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
             if (FINAL) {
 #pragma unroll
                 for (int py = 0; py < 2; ++py) {
-                    const int gyc = min(y0 + 2 * my + py, Ho - 1);
+                    const int gyc = INTERIOR ? y0 + 2 * my + py : min(y0 + 2 * my + py, Ho - 1);
                     pixc[py] = (unsigned)(gyc * Wo);
                     const IN_T* rowp = img_z + pixc[py];
                     px[py].load(rowp + (VEC ? gxc : 0), VEC ? 0 : gxc, gx1c);
@@ -1492,7 +1490,7 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
                     v1 = fmaf(fl, L1[sl], v1);
                     v1 = fmaf(fh, G1[sl], v1);
                 }
-                const bool row_ok = (gy < Ho) && v0ok;
+                const bool row_ok = INTERIOR || ((gy < Ho) && v0ok);
                 if (!FINAL) {
                     // pitch_o is a multiple of 4 and gx is even: the pair store stays inside the row
                     if (row_ok) store_pair(outA_z + (unsigned)(gy * pitch_o), v0, v1);
@@ -1529,6 +1527,28 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
             }
         }
     }
+}
+
+template <bool FINAL, typename IN_T, typename OUT_T, bool VEC>
+__global__ void __launch_bounds__(SY_THREADS, DSTR_SY_MINB)
+synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl, int Wl, int pitch_l,
+             size_t pstride_l, float* __restrict__ outA, int Ho, int Wo, int pitch_o,
+             size_t pstride_o, const IN_T* __restrict__ img, OUT_T* __restrict__ out,
+             size_t img_pstride, EpilogueArgs ep) {
+    const int wid = threadIdx.x >> 5;
+    const int x0 = (blockIdx.x * SY_WARPS + wid) * SY_TX;
+    const int y0 = blockIdx.y * SY_TY;
+    if (x0 >= Wo) return;  // no block-level synchronisation below
+    // the big final kernel gets a predicate-free path for tiles away from the right / bottom borders:
+    // coefficient columns x0/2 .. x0/2 + 33, coefficient rows y0/2 .. y0/2 + SY_TY/2 + 3, SY_TX x SY_TY pixels
+    const bool interior = FINAL && (x0 + SY_TX <= Wo) && ((x0 >> 1) + 34 <= Wl) && (y0 + SY_TY <= Ho) &&
+                          ((y0 >> 1) + SY_TY / 2 + 4 <= Hl);
+    if (interior)
+        synth_tile<FINAL, IN_T, OUT_T, VEC, true>(dA, dH, Hl, Wl, pitch_l, pstride_l, outA, Ho, Wo, pitch_o, pstride_o,
+                                                  img, out, img_pstride, ep, x0, y0);
+    else
+        synth_tile<FINAL, IN_T, OUT_T, VEC, false>(dA, dH, Hl, Wl, pitch_l, pstride_l, outA, Ho, Wo, pitch_o, pstride_o,
+                                                   img, out, img_pstride, ep, x0, y0);
 }
 
 // standalone flatfield_correction (filtering.py:338-414): elementwise over n_outer x n_inner
