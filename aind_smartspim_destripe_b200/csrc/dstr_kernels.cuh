@@ -518,6 +518,7 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
     float* oA = cA + (size_t)z * out_pstride + (size_t)oy0 * out_pitch + gox;
     float* oH = cH + (size_t)z * out_pstride + (size_t)oy0 * out_pitch + gox;
 
+    ptrdiff_t row_off = -2 * (ptrdiff_t)out_pitch;  // output row 3 s + k - 2 of stage s, k = 0
     for (int s = 0; s < n_stages; ++s) {
         __syncthreads();  // every warp is done with stage s-1: its slot may be refilled
         if (tid == 0 && s + AT_STAGES - 1 < n_stages) issue_stage(s + AT_STAGES - 1);
@@ -576,14 +577,18 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
             ch = fmaf(dec_lo(3), d0m1, ch);
             ch = fmaf(dec_lo(4), d1m2, ch);
             ch = fmaf(dec_lo(5), d0m2, ch);
-            if (col_ok && oy >= 0 && oy < R) {
-                oA[(size_t)oy * out_pitch] = ca;
-                oH[(size_t)oy * out_pitch] = ch;
-                const float q = __fmul_rn(ch, ch);
-                qmin = fminf(qmin, q);
-                qmax = fmaxf(qmax, q);
+            // predicated stores through a running row offset (no branch, no 64-bit multiply per row)
+            const bool ok = col_ok && (unsigned)oy < (unsigned)R;
+            const ptrdiff_t ro = row_off + k * (ptrdiff_t)out_pitch;
+            if (ok) {
+                oA[ro] = ca;
+                oH[ro] = ch;
             }
+            const float q = __fmul_rn(ch, ch);
+            qmin = ok ? fminf(qmin, q) : qmin;
+            qmax = ok ? fmaxf(qmax, q) : qmax;
         }
+        row_off += 3 * (ptrdiff_t)out_pitch;
     }
 
     // block reductions -> one set of atomics per block
@@ -1539,7 +1544,8 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
     const int x0 = (blockIdx.x * SY_WARPS + wid) * SY_TX;
     const int y0 = blockIdx.y * SY_TY;
     if (x0 >= Wo) return;  // no block-level synchronisation below
-    // the big final kernel gets a predicate-free path for tiles away from the right / bottom borders:
+    // the big final kernel gets a predicate-free path for tiles away from the right / bottom borders
+    // (no measurable gain for the small deep-level launches):
     // coefficient columns x0/2 .. x0/2 + 33, coefficient rows y0/2 .. y0/2 + SY_TY/2 + 3, SY_TX x SY_TY pixels
     const bool interior = FINAL && (x0 + SY_TX <= Wo) && ((x0 >> 1) + 34 <= Wl) && (y0 + SY_TY <= Ho) &&
                           ((y0 >> 1) + SY_TY / 2 + 4 <= Hl);
