@@ -367,13 +367,14 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
                 ch = fmaf(dec_lo(3), d0m1, ch);
                 ch = fmaf(dec_lo(4), d1m2, ch);
                 ch = fmaf(dec_lo(5), d0m2, ch);
-                if (col_ok && oy0 + oy < Ho) {
+                const bool ok = col_ok && oy0 + oy < Ho;
+                if (ok) {
                     *oA = ca;
                     *oH = ch;
-                    const float q = __fmul_rn(ch, ch);
-                    qmin = fminf(qmin, q);
-                    qmax = fmaxf(qmax, q);
                 }
+                const float q = __fmul_rn(ch, ch);
+                qmin = ok ? fminf(qmin, q) : qmin;
+                qmax = ok ? fmaxf(qmax, q) : qmax;
                 oA += out_pitch;
                 oH += out_pitch;
             }
