@@ -1136,15 +1136,22 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
             int t = (tau_lo + lane) % n;
             if (t < 0) t += n;
             const int step = 32 % n;
+            // the row pointer is materialised once (one wide multiply-add per load instead of a 64-bit
+            // index chain); stores are predicated on clamped indices, no branches in the loop
+            const float* gp = grow;
+            asm volatile("" : "+l"(gp));
+            int ae = tau_lo + lane + OFFe, ao = tau_lo + lane + OFFo;
             DSTR_UNROLL(DSTR_BUILD_UNROLL)
-            for (int tau = tau_lo + lane; tau < tau_hi && !(abl & 64); tau += 32) {
-                const int tr = (t == 0) ? 0 : n - t;
-                const float c1 = grow[t], c2 = grow[tr];
+            for (int tau = tau_lo + lane; tau < tau_hi && !(abl & 64); tau += 32, ae += 32, ao += 32) {
+                const unsigned tr = (t == 0) ? 0u : (unsigned)(n - t);
+                const float c1 = gp[(unsigned)t], c2 = gp[tr];
                 const float x1 = (__fmul_rn(c1, c1) > thr_q) ? med : c1;
                 const float x2 = (__fmul_rn(c2, c2) > thr_q) ? med : c2;
-                const int ae = tau + OFFe, ao = tau + OFFo;
-                if (ae >= 0 && ae < len_e) E[ae + (ae >> 3)] = 0.5f * (x1 + x2);
-                if (ao >= 0 && ao < len_o) O[ao + (ao >> 3)] = 0.5f * (x1 - x2);
+                const bool pe = (unsigned)ae < (unsigned)len_e, po = (unsigned)ao < (unsigned)len_o;
+                const int ie = pe ? ae + (ae >> 3) : 0, io = po ? ao + (ao >> 3) : 0;
+                const float ve = 0.5f * (x1 + x2), vo = 0.5f * (x1 - x2);
+                if (pe) E[ie] = ve;
+                if (po) O[io] = vo;
                 t += step;
                 if (t >= n) t -= n;
             }
