@@ -901,6 +901,11 @@ __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float(b);
 }
 
+#ifndef DSTR_FIR_UNROLL
+#define DSTR_FIR_UNROLL 1
+#endif
+#define DSTR_PRAGMA(x) _Pragma(#x)
+#define DSTR_UNROLL(n) DSTR_PRAGMA(unroll n)
 // acc[i] += sum_k taps[k] * Xlog[8*m0 + i - k],  k = 0..ntap-1 (ntap % 8 == 0).
 // Logical element a = 8 b + i lives at Xphys[BS * b + ES * i]  (padded rows: ES 1, BS 9).
 template <int ES, int BS>
@@ -911,6 +916,7 @@ __device__ __forceinline__ void fir8(float (&acc)[8], const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = Xp[ES * i];
     const float4* t4 = reinterpret_cast<const float4*>(taps);
+    DSTR_UNROLL(DSTR_FIR_UNROLL)
     for (int kk = 0; kk < ntap / 8; ++kk) {
         const float4 ta = t4[2 * kk], tb = t4[2 * kk + 1];
         const float tk[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
@@ -983,8 +989,6 @@ template <int EPL>
 #ifndef DSTR_LR2_UNROLL
 #define DSTR_LR2_UNROLL 2
 #endif
-#define DSTR_PRAGMA(x) _Pragma(#x)
-#define DSTR_UNROLL(n) DSTR_PRAGMA(unroll n)
 __global__ void __launch_bounds__(FR_THREADS, (EPL <= 33 ? DSTR_FR_MINB : 4))
 filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
