@@ -94,6 +94,8 @@ struct dstr_ctx {
     bool overlap = true;
     bool use_tma = true;  // level-1 analysis through the TMA-staged kernel when the plane shape allows
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    unsigned long long host_it = 0;  // sub-chunks streamed so far (staging buffer = host_it & 1), across calls
+    bool async_pending = false;      // a DSTR_FLAG_NO_SYNC call with host buffers is still in flight
     float fg_half_thr = 384.f;
     float fg_thr32 = 384.f;  // the same rule on the float32 value (fg_threshold_f32)
     double notch_eps = 1e-6;  // truncation tolerance of the hybrid notch operator (0 = dense)
@@ -1083,9 +1085,24 @@ int dstr_destroy(dstr_ctx* ctx) {
     return 0;
 }
 
+// Work enqueued by an asynchronous host-buffer call must finish before anything else touches the
+// staging buffers, the workspace or the tables.
+static int drain_async(dstr_ctx* ctx) {
+    if (!ctx->async_pending) return 0;
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    ctx->async_pending = false;
+    return 0;
+}
+
 int dstr_set_flat_dark(dstr_ctx* ctx, const float* flat, const float* dark) {
     if (!ctx) return DSTR_E_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
     if (!flat || !dark) {
         ctx->have_flat_dark = false;
         return 0;
@@ -1172,6 +1189,14 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
         return fail(ctx, DSTR_E_SHAPE, "stack-wide Otsu needs the whole chunk within max_planes");
 
     const bool pyramid = ctx->pyr_out[0] != nullptr;
+    // DSTR_FLAG_NO_SYNC with host buffers: the copies and kernels are enqueued and the call returns; the
+    // staging buffers are handed from call to call through the same events, so the H2D of the next chunk
+    // overlaps the D2H of this one.  The caller owns both host buffers until dstr_synchronize.
+    const bool async = (flags & DSTR_FLAG_NO_SYNC) && !ctx->profiling && !pyramid && !stack && !in_dev && !out_dev;
+    if (!async) {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
     if (pyramid) {
         if (out_dtype != DSTR_U16) return fail(ctx, DSTR_E_ARG, "pyramid outputs need a uint16 chunk output");
         if (ctx->zcap < 4) return fail(ctx, DSTR_E_STATE, "pyramid outputs need max_planes >= 4");
@@ -1213,10 +1238,10 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
     if (stack) sub = Z;
     rc = ensure_stage(ctx, sub);
     if (rc) return rc;
-    int it = 0;
-    for (int z0 = 0; z0 < Z; z0 += sub, ++it) {
+    for (int z0 = 0; z0 < Z; z0 += sub, ++ctx->host_it) {
         const int zn = std::min(sub, Z - z0);
-        const int b = it & 1;
+        const unsigned long long it = ctx->host_it;
+        const int b = (int)(it & 1);
         const void* src = (const char*)in + (size_t)z0 * in_pb;
         void* dst = (char*)out + (size_t)z0 * out_pb;
         const void* dsrc = src;
@@ -1253,9 +1278,14 @@ int dstr_filter_chunk(dstr_ctx* ctx, const void* in, int in_dtype, void* out, in
             CK(ctx, cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
         }
     }
+    if (async) {
+        ctx->async_pending = true;
+        return 0;
+    }
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
     CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    ctx->async_pending = false;
     resolve_timers(ctx);
     return 0;
 }
@@ -1266,6 +1296,10 @@ int dstr_plane_stats(dstr_ctx* ctx, const void* in, int in_dtype, int Z, double*
     if (!in || Z <= 0 || !fg_mean || !bg_mean) return fail(ctx, DSTR_E_ARG, "dstr_plane_stats: bad argument");
     if (in_dtype != DSTR_U16 && in_dtype != DSTR_F32) return fail(ctx, DSTR_E_ARG, "bad dtype");
     CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
     const bool in_dev = is_device_ptr(in);
     const size_t plane_px = (size_t)ctx->H * ctx->W;
     const size_t in_pb = plane_px * dtype_size(in_dtype);
@@ -1408,6 +1442,7 @@ int dstr_synchronize(dstr_ctx* ctx) {
     CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    ctx->async_pending = false;
     resolve_timers(ctx);
     return 0;
 }
@@ -1498,6 +1533,10 @@ int dstr_set_pyramid_outputs(dstr_ctx* ctx, void* level1, void* level2) {
 int dstr_downscale2x(dstr_ctx* ctx, const uint16_t* in, int Z, int H, int W, uint16_t* out) {
     if (!ctx || !in || !out || Z < 2 || H < 2 || W < 2) return fail(ctx, DSTR_E_ARG, "dstr_downscale2x: bad argument");
     CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
     const size_t n_in = (size_t)Z * H * W, n_out = (size_t)(Z / 2) * (H / 2) * (W / 2);
     const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
     uint16_t *d_in = (uint16_t*)in, *d_out = out;
@@ -1545,6 +1584,10 @@ int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_
     if (!ctx || !host_buf) return DSTR_E_ARG;
     if (level < 1 || level > ctx->Lalloc) return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: bad level");
     CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     const int Z = ctx->last_z;
     const LevelGeom& g = ctx->geom[level];

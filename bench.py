@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="issue every kernel on one stream in stage order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sync", action="store_true", help="wait for every step's result before submitting the next")
     return ap.parse_args()
 
 
@@ -312,22 +313,33 @@ def run_b200(args):
     if not args.no_e2e:
         pin_in = E.PinnedBuffer((Z, H, W), np.uint16)
         pin_out = E.PinnedBuffer((Z, H, W), np.uint16)
+        pin_out2 = E.PinnedBuffer((Z, H, W), np.uint16)
         pin_in.array[...] = stack
         if args.subchunk:
             eng.set_subchunk(args.subchunk)
         for _ in range(2):
             eng.filter_chunk(pin_in.array, pn, cells=pc, out=pin_out.array, high_int=HIGH_INT, mode=mode, flags=flags)
+        # Every step copies its chunk host -> device and its result device -> host through the public call.
+        # Steps are submitted without waiting (DSTR_FLAG_NO_SYNC on pinned host buffers, results alternating
+        # between two host buffers), so the upload of step k+1 overlaps the download of step k, as a caller
+        # streaming chunks does; the clock stops after the last result is on the host.
+        outs = [pin_out.array, pin_out2.array]
         D.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.filter_chunk(pin_in.array, pn, cells=pc, out=pin_out.array, high_int=HIGH_INT, mode=mode, flags=flags)
+        for k in range(args.steps):
+            eng.filter_chunk(pin_in.array, pn, cells=pc, out=outs[k & 1], high_int=HIGH_INT, mode=mode,
+                             flags=flags | (0 if args.e2e_sync else E.FLAG_NO_SYNC))
+        eng.synchronize()
         dt = time.perf_counter() - t0
         dt = D.max_over_ranks(dt)
+        if args.steps > 1 and not np.array_equal(outs[0][::17, ::64, ::64], outs[1][::17, ::64, ::64]):
+            raise RuntimeError("e2e: the two result buffers differ")
         # result check-sum read back on the host (the step's result is consumed)
         checksum = int(pin_out.array[:: max(1, Z // 4), ::64, ::64].astype(np.int64).sum())
         e2e = {"value": world * px_per_step * args.steps / dt / 1e6, "unit": "Mpixel/s",
                "h2d_bytes_per_step": int(stack.nbytes), "d2h_bytes_per_step": int(stack.nbytes),
-               "ms_per_step": 1e3 * dt / args.steps, "checksum": checksum}
+               "ms_per_step": 1e3 * dt / args.steps, "checksum": checksum,
+               "submission": "synchronous" if args.e2e_sync else "asynchronous (DSTR_FLAG_NO_SYNC, 2 result buffers)"}
         # the ceiling of this figure: concurrent pinned H2D + D2H copies of the same buffers, nothing else
         if rank == 0 and world == 1:
             try:
@@ -358,6 +370,7 @@ def run_b200(args):
                 e2e["pcie_probe_error"] = str(exc)
         pin_in.free()
         pin_out.free()
+        pin_out2.free()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------
     cpu = None

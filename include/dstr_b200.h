@@ -43,7 +43,9 @@ typedef struct dstr_ctx dstr_ctx;
 #define DSTR_FLAG_EXPM1 2       /* corrected inverse exp(y)-1 instead of the reference's exp(y)+1 */
 #define DSTR_FLAG_STACK_OTSU 4  /* 3-D input semantics: one Otsu threshold per level for the whole
                                    chunk (filtering.py:182-183,210-213)                          */
-#define DSTR_FLAG_NO_SYNC 8     /* device buffers only: enqueue and return without synchronising */
+#define DSTR_FLAG_NO_SYNC 8     /* enqueue and return without synchronising (device buffers, or pinned
+                                   host buffers: both stay owned by the call until dstr_synchronize; the
+                                   next chunk's H2D then overlaps this chunk's D2H) */
 
 /* Filter parameters = the reference's config dict {wavelet:"db3", level, sigma, max_threshold}
  * (run_capsule.py:377-388).  level < 0 means "None" (maximum level). */

@@ -338,3 +338,31 @@ def test_destripe_channel_picks_flat_by_laser_side(tmp_path, production_configs)
     with pytest.raises(ValueError):
         zd.destripe_channel(data, deriv, "Ex_488_Em_525", tmp_path / "r2", [1.8, 1.8, 2.0], flat_paths,
                             {"0": ["100_200"]}, params)
+
+
+def test_asynchronous_host_chunks_match_synchronous_calls(production_configs):
+    # DSTR_FLAG_NO_SYNC with pinned host buffers: chunks are queued back to back, results are valid after synchronize()
+    no_cells, cells = production_configs
+    H, W = 160, 192
+    eng = E.DestripeEngine(H, W, max_planes=8)
+    f, d = S.synthetic_flat_dark(H, W)
+    eng.set_flat_dark(f, d)
+    chunks = [S.synthetic_stack(10, H, W, base_seed=300 + 20 * k, cells_every=3) for k in range(3)]
+    pn, pc = E.make_params(no_cells), E.make_params(cells)
+    ref = [eng.filter_chunk(c, pn, cells=pc, high_int=2500, mode=E.MODE_DISPATCH, flags=E.FLAG_SHADOW) for c in chunks]
+    pins = [E.PinnedBuffer(c.shape, np.uint16) for c in chunks]
+    outs = [E.PinnedBuffer(c.shape, np.uint16) for c in chunks]
+    for p, c in zip(pins, chunks):
+        p.array[...] = c
+    for p, o in zip(pins, outs):
+        eng.filter_chunk(p.array, pn, cells=pc, out=o.array, high_int=2500, mode=E.MODE_DISPATCH,
+                         flags=E.FLAG_SHADOW | E.FLAG_NO_SYNC)
+    # another entry point drains the queue first instead of racing with it
+    fg, bg, uc = eng.plane_stats(chunks[0], high_int=2500)
+    eng.synchronize()
+    for o, r in zip(outs, ref):
+        np.testing.assert_array_equal(o.array, r)
+    assert len(fg) == 10
+    for b in pins + outs:
+        b.free()
+    eng.close()
