@@ -355,13 +355,16 @@ def run_b200(args):
                     with torch.cuda.stream(s2):
                         t_out.copy_(g_out, non_blocking=True)
 
-                both()
-                torch.cuda.synchronize()
-                tc = time.perf_counter()
-                for _ in range(3):
+                for _ in range(2):
                     both()
                 torch.cuda.synchronize()
-                gbps = 3 * t_in.numel() / (time.perf_counter() - tc) / 1e9
+                gbps = 0.0
+                for _ in range(3):  # best of three bursts of four copy pairs
+                    tc = time.perf_counter()
+                    for _ in range(4):
+                        both()
+                    torch.cuda.synchronize()
+                    gbps = max(gbps, 4 * t_in.numel() / (time.perf_counter() - tc) / 1e9)
                 e2e["pcie_bidirectional_GBps_each"] = gbps
                 e2e["pcie_ceiling_Mpixel_per_s"] = gbps * 1e9 / 2 / 1e6
                 e2e["frac_of_pcie_ceiling"] = e2e["value"] / e2e["pcie_ceiling_Mpixel_per_s"]
