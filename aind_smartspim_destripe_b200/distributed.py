@@ -31,9 +31,11 @@ def init(backend: str = None) -> Tuple[int, int, int]:
             os.environ.setdefault("MASTER_PORT", "29511")
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
+            kwargs = {}
             if backend == "nccl":
                 torch.cuda.set_device(local)
-            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+                kwargs["device_id"] = torch.device(f"cuda:{local}")  # no rank -> GPU guessing at the first barrier
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     return rank, world, local
 
 
