@@ -284,8 +284,9 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
     const bool own0 = (lane >= 2) && (gx0 < Ws);  // pixel ownership for the plane statistics
     const bool own1 = (lane >= 2) && (gx1 < Ws);
 
-    float fg_s = 0.f, all_s = 0.f;  // per-thread partial sums (<= 96 pixels: exact for integers)
-    unsigned fg_c = 0, all_c = 0;
+    float fg_s = 0.f, all_s = 0.f;  // per-thread, per-column partial sums (<= 48 pixels each: exact for integers)
+    float fg_s1 = 0.f, all_s1 = 0.f;
+    unsigned fg_c = 0, fg_c1 = 0, all_c = 0;  // all_c counts rows: both columns share it
     float qmin = __int_as_float(0x7f800000), qmax = 0.f;
 
     if (ox0 < Wo && oy0 < Ho) {  // warp-uniform
@@ -305,14 +306,19 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
                 if (STATS) {
                     const int gy0 = 2 * oy0 - 4 + r;
                     if (r >= 4 && gy0 < Hs) {  // rows owned by this tile: [2 oy0, 2 oy0 + 2 AN_TOY)
-                        const bool f0 = own0 && (v0 >= fg_thr32);
-                        const bool f1 = own1 && (v1 >= fg_thr32);
-                        all_s += own0 ? v0 : 0.f;
-                        all_s += own1 ? v1 : 0.f;
-                        all_c += (own0 ? 1u : 0u) + (own1 ? 1u : 0u);
-                        fg_s += f0 ? v0 : 0.f;
-                        fg_s += f1 ? v1 : 0.f;
-                        fg_c += (f0 ? 1u : 0u) + (f1 ? 1u : 0u);
+                        // per-column accumulators, no ownership selects in the loop: lanes / columns that
+                        // belong to a neighbour are masked once at the end
+                        all_s += v0;
+                        all_s1 += v1;
+                        ++all_c;
+                        if (v0 >= fg_thr32) {
+                            fg_s += v0;
+                            ++fg_c;
+                        }
+                        if (v1 >= fg_thr32) {
+                            fg_s1 += v1;
+                            ++fg_c1;
+                        }
                     }
                 }
                 v0 = DSTR_LOGF(__fadd_rn(1.0f, v0));  // np.log(1.0 + x) in float32
@@ -389,9 +395,11 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
         s_red[1][wid] = qmax;
     }
     if (FIRST && STATS) {
-        const double fs = warp_sum((double)fg_s), as = warp_sum((double)all_s);
-        fg_c = __reduce_add_sync(0xffffffffu, fg_c);
-        all_c = __reduce_add_sync(0xffffffffu, all_c);
+        // ownership mask applied once per lane and column
+        const double fs = warp_sum((own0 ? (double)fg_s : 0.0) + (own1 ? (double)fg_s1 : 0.0));
+        const double as = warp_sum((own0 ? (double)all_s : 0.0) + (own1 ? (double)all_s1 : 0.0));
+        fg_c = __reduce_add_sync(0xffffffffu, (own0 ? fg_c : 0u) + (own1 ? fg_c1 : 0u));
+        all_c = __reduce_add_sync(0xffffffffu, all_c * ((own0 ? 1u : 0u) + (own1 ? 1u : 0u)));
         if (lane == 0) {
             s_dred[0][wid] = fs;
             s_dred[1][wid] = as;
@@ -510,8 +518,8 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
         for (int s = 0; s < AT_STAGES - 1 && s < n_stages; ++s) issue_stage(s);
     }
 
-    float fg_s = 0.f, all_s = 0.f;
-    unsigned fg_c = 0, all_c = 0;
+    float fg_s = 0.f, all_s = 0.f, fg_s1 = 0.f, all_s1 = 0.f;  // per column of the lane's pixel pair
+    unsigned fg_c = 0, fg_c1 = 0, all_c = 0;                  // all_c counts rows: both columns share it
     float qmin = __int_as_float(0x7f800000), qmax = 0.f;
     float w0[6], w1[6];
     const int gox = ox0 + lane - 2;
@@ -538,14 +546,19 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
                 if (STATS) {
                     const int gy0 = 2 * oy0 - 4 + r;
                     if (r >= 4 && r < 4 + 2 * R && gy0 < Hs) {  // rows owned by this CTA
-                        const bool f0 = own0 && (v0 >= fg_thr32);
-                        const bool f1 = own1 && (v1 >= fg_thr32);
-                        all_s += own0 ? v0 : 0.f;
-                        all_s += own1 ? v1 : 0.f;
-                        all_c += (own0 ? 1u : 0u) + (own1 ? 1u : 0u);
-                        fg_s += f0 ? v0 : 0.f;
-                        fg_s += f1 ? v1 : 0.f;
-                        fg_c += (f0 ? 1u : 0u) + (f1 ? 1u : 0u);
+                        // per-column accumulators, no ownership selects in the loop: lanes / columns that
+                        // belong to a neighbour are masked once at the end
+                        all_s += v0;
+                        all_s1 += v1;
+                        ++all_c;
+                        if (v0 >= fg_thr32) {
+                            fg_s += v0;
+                            ++fg_c;
+                        }
+                        if (v1 >= fg_thr32) {
+                            fg_s1 += v1;
+                            ++fg_c1;
+                        }
                     }
                 }
                 w0[2 * k + h] = DSTR_LOGF(__fadd_rn(1.0f, v0));  // np.log(1.0 + x) in float32
@@ -600,9 +613,11 @@ analysis_tma_kernel(const IN_T* __restrict__ in, int Hs, int Ws, size_t in_pstri
         s_red[1][wid] = qmax;
     }
     if (STATS) {
-        const double fs = warp_sum((double)fg_s), as = warp_sum((double)all_s);
-        fg_c = __reduce_add_sync(0xffffffffu, fg_c);
-        all_c = __reduce_add_sync(0xffffffffu, all_c);
+        // ownership mask applied once per lane and column
+        const double fs = warp_sum((own0 ? (double)fg_s : 0.0) + (own1 ? (double)fg_s1 : 0.0));
+        const double as = warp_sum((own0 ? (double)all_s : 0.0) + (own1 ? (double)all_s1 : 0.0));
+        fg_c = __reduce_add_sync(0xffffffffu, (own0 ? fg_c : 0u) + (own1 ? fg_c1 : 0u));
+        all_c = __reduce_add_sync(0xffffffffu, all_c * ((own0 ? 1u : 0u) + (own1 ? 1u : 0u)));
         if (lane == 0) {
             s_dred[0][wid] = fs;
             s_dred[1][wid] = as;
