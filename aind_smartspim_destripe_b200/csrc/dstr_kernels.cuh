@@ -1533,10 +1533,9 @@ __device__ __forceinline__ void synth_tile(const float* __restrict__ dA, const f
                     float r0 = fmaf(__fadd_rn(1.0f, xin0), DSTR_EXPF(v0), one);
                     float r1 = fmaf(__fadd_rn(1.0f, xin1), DSTR_EXPF(v1), one);
                     if (ep.shadow) {  // flatfield_correction, filtering.py:399-412
-                        r0 = (r0 <= dk[py][0]) ? 0.f : (r0 - dk[py][0]);
-                        r1 = (r1 <= dk[py][1]) ? 0.f : (r1 - dk[py][1]);
-                        r0 *= ifl[py][0];
-                        r1 *= ifl[py][1];
+                        // where(r <= dark, 0, r - dark) == max(r - dark, 0) for finite values
+                        r0 = fmaxf(r0 - dk[py][0], 0.f) * ifl[py][0];
+                        r1 = fmaxf(r1 - dk[py][1], 0.f) * ifl[py][1];
                     }
                     if (sizeof(OUT_T) == 2 || ep.shadow) {
                         r0 = fminf(fmaxf(r0, 0.f), 65535.f);  // np.clip; the u16 conversion truncates

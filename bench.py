@@ -99,6 +99,7 @@ class ClockSampler:
         self.stop_flag = threading.Event()
         self.thread = None
         self.source = None
+        self._nv = None
 
     def _nvml_handle(self):
         import pynvml
@@ -139,9 +140,26 @@ class ClockSampler:
             except Exception:
                 time.sleep(0.01)
 
+    def sample_now(self):
+        """One synchronous sample from the calling thread (NVML only)."""
+        if self._nv is None:
+            return
+        nv, h = self._nv
+        try:
+            mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            bits = [(nv.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                    (nv.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                    (nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                    (nv.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+            self.samples.append((float(mhz), [nm for bit, nm in bits if mask & bit]))
+        except Exception:
+            pass
+
     def start(self):
         try:
             nv, h = self._nvml_handle()
+            self._nv = (nv, h)
             self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self.source = "nvml"
             self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
@@ -273,6 +291,8 @@ def run_b200(args):
     for _ in range(args.steps):
         step_resident()
     ev1.record(stream)
+    if rank == 0:
+        sampler.sample_now()  # the steps are enqueued and still running: at least one sample under load
     eng.synchronize()
     torch.cuda.synchronize()
     D.barrier()
