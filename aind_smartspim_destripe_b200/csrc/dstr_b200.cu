@@ -3,6 +3,7 @@
 // replaces the reference's multiprocessing producer/consumer
 // (/root/reference/code/aind_smartspim_destripe/zarr_destriper.py:797-906).
 #include "dstr_kernels.cuh"
+#include "dstr_notch_umma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -50,6 +51,17 @@ struct NotchDevice {
     double eps = -1.0;
     float* d_buf = nullptr;  // one allocation: te | to | T1 | T2
     NotchTables nt = {};
+    // tcgen05 path (dstr_notch_umma.cuh): fp16 hi / lo Hankel tables [TBh | TBl | TRh | TRl]
+    uint4* d_umma = nullptr;
+    int um_Rb = 0, um_r3 = 0;
+    unsigned long long um_need = 0;
+};
+
+// Geometry of the tcgen05 row filter for a band of width n (depends on n only).
+struct UmmaGeom {
+    int nh = 0, nout = 0, P = 0, Nt = 0, NC = 0, Kpad = 0, tab_bytes = 0, mw = 0, xs_stride = 0;
+    size_t smem = 0;
+    bool ok = false;
 };
 
 struct TapTable {
@@ -93,6 +105,11 @@ struct dstr_ctx {
     cudaEvent_t ev_an[kMaxLevels + 1] = {}, ev_flt[kMaxLevels + 1] = {};
     bool overlap = true;
     bool use_tma = true;  // level-1 analysis through the TMA-staged kernel when the plane shape allows
+    bool use_umma = true;  // row filter on tcgen05 where the band geometry allows (dstr_notch_umma.cuh)
+    // per-CTA operand scratch of the tcgen05 row filter, one per level (the levels' filters run
+    // concurrently on the side streams)
+    uint8_t* d_um_scratch[kMaxLevels + 1] = {};
+    size_t um_scratch_bytes[kMaxLevels + 1] = {};
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     unsigned long long host_it = 0;  // sub-chunks streamed so far (staging buffer = host_it & 1), across calls
     bool async_pending = false;      // a DSTR_FLAG_NO_SYNC call with host buffers is still in flight
@@ -104,6 +121,7 @@ struct dstr_ctx {
     int debug_stop = DSTR_STAGE_NONE;
     int last_levels = 0;
     int last_z = 0;
+    DispatchParams last_dp = {};  // dispatch rule of the last pass (dstr_debug_fetch reports use_cells)
     double timers[DSTR_NUM_TIMERS] = {};
     uint64_t launches = 0;
     std::vector<TimerSpan> spans;
@@ -438,6 +456,97 @@ void design_notch(int n, double s, double eps, NotchHost& out) {
     }
 }
 
+// ---- tcgen05 row filter: geometry and tables (dstr_notch_umma.cuh) ---------------------------
+UmmaGeom umma_geom(int n) {
+    UmmaGeom g;
+    g.nh = n / 2;
+    g.nout = g.nh + 1;
+    g.P = (g.nout + 255) / 256;
+    g.Nt = (((g.nout + g.P - 1) / g.P) + 15) & ~15;
+    g.NC = (n + UM_KC - 1) / UM_KC;
+    g.Kpad = UM_KC * g.NC;
+    const int L = g.P * g.Nt + g.Kpad + 8;  // largest u + v (+ the 7 shifted copies)
+    g.tab_bytes = ((((L + 7) / 8) * 128) + 1023) & ~1023;
+    g.mw = g.NC;
+    g.xs_stride = g.Kpad + 4;  // = 4 (mod 32): the 8 rows of a 128-bit staging load hit 32 distinct banks
+    const size_t ring = (size_t)UM_STAGES * 4 * UM_CHUNK_BYTES;
+    g.smem = (size_t)4 * g.tab_bytes + ring + (size_t)UM_ROWS * g.mw * 4;
+    const size_t staging = (size_t)2 * UM_BATCH * g.xs_stride * 4;
+    g.ok = n >= 96 && n <= 32 * 33 && g.NC <= 64 && g.smem <= (size_t)226 * 1024 && staging <= ring && g.Nt <= 256;
+    return g;
+}
+
+uint16_t half_bits(float v) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const uint16_t*>(&h);
+}
+float half_value(uint16_t b) {
+    __half_raw hr;
+    hr.x = b;
+    return __half2float(__half(hr));
+}
+
+// Tables of one (band width n, notch width s): T[blk][r][e] = f(8 blk + r + e) for the periodic
+// sequences f = 256 * 1/2 hb restricted to circular distance <= Rb ("TB") and f = 256 * 1/2 (ha - that)
+// ("TR"; the full ha when the remainder needs the three-product split anyway), as fp16 hi and lo.
+struct UmmaHost {
+    std::vector<uint16_t> tabs;  // [TBh | TBl | TRh | TRl], tab_bytes / 2 halfs each
+    int Rb = 0, r3 = 0;
+    unsigned long long need = 0;
+};
+
+void build_umma_host(int n, double s, const UmmaGeom& g, UmmaHost& out) {
+    const int nh = n / 2;
+    const int Jn = (n % 2 == 0) ? nh + 1 : (n + 1) / 2;
+    auto w = [&](double k) { return std::exp(-(k * k) / (2.0 * s * s)); };
+    std::vector<double> ct(n);
+    for (int i = 0; i < n; ++i) ct[i] = std::cos(2.0 * M_PI * (double)i / (double)n);
+    std::vector<double> a(Jn), b(Jn), ha, hb;
+    for (int j = 0; j < Jn; ++j) {
+        a[j] = (j == 0) ? w(0) : w(2.0 * j - 1.0);
+        b[j] = w(2.0 * j);
+    }
+    if (n % 2 == 0) a[nh] = w(n - 1.0);
+    idft_even(n, a, ct, ha);
+    idft_even(n, b, ct, hb);
+    // band radius: the odd part is hb alone, so its truncated tail (relative L1 mass 2e-7) is the
+    // truncation error of the operator; for the even part the cut goes into the remainder exactly
+    int Rb = tail_radius(n, hb, 2e-7);
+    if (2 * Rb + 1 >= n) Rb = nh;
+    std::vector<double> fb(n), fr(n);
+    double r2 = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const int d = std::min(k, n - k);
+        fb[k] = (d <= Rb) ? hb[k] : 0.0;
+        fr[k] = ha[k] - fb[k];
+        r2 += fr[k] * fr[k];
+    }
+    out.Rb = Rb;
+    out.r3 = std::sqrt(r2) > 0.004 ? 1 : 0;  // single-product error ~ |r|_2 2^-12 |x|
+    if (out.r3)
+        for (int k = 0; k < n; ++k) fr[k] = ha[k];  // E runs entirely on the split remainder table
+    const size_t th = (size_t)g.tab_bytes / 2;
+    out.tabs.assign(4 * th, 0);
+    const int nblk = g.tab_bytes / 128;
+    for (int blk = 0; blk < nblk; ++blk)
+        for (int r = 0; r < 8; ++r)
+            for (int e = 0; e < 8; ++e) {
+                const int k = (8 * blk + r + e) % n;
+                const size_t o = (size_t)blk * 64 + r * 8 + e;
+                const float vb = (float)(0.5 * fb[k] * (double)UM_TABLE_SCALE);
+                const float vr = (float)(0.5 * fr[k] * (double)UM_TABLE_SCALE);
+                const uint16_t bh = half_bits(vb), rh = half_bits(vr);
+                out.tabs[o] = bh;
+                out.tabs[th + o] = half_bits(vb - half_value(bh));
+                out.tabs[2 * th + o] = rh;
+                out.tabs[3 * th + o] = half_bits(vr - half_value(rh));
+            }
+    out.need = 0;
+    for (int p = 0; p < g.P; ++p)
+        for (int c = 0; c < g.NC; ++c)
+            if (um_band(p * g.Nt, g.Nt, c, n, Rb)) out.need |= 1ull << c;
+}
+
 int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     NotchDevice& D = ctx->taps[level].cfg[cfg];
     if (D.d_buf && D.sigma == sigma && D.eps == ctx->notch_eps) return 0;
@@ -475,6 +584,23 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     D.nt.Jpad = hst.Jpad;
     D.sigma = sigma;
     D.eps = ctx->notch_eps;
+    {
+        const UmmaGeom g = umma_geom(n);
+        if (D.d_umma) {
+            cudaFree(D.d_umma);
+            D.d_umma = nullptr;
+        }
+        if (g.ok) {
+            UmmaHost uh;
+            build_umma_host(n, s, g, uh);
+            CK(ctx, cudaMalloc(&D.d_umma, (size_t)4 * g.tab_bytes));
+            CK(ctx, cudaMemcpyAsync(D.d_umma, uh.tabs.data(), (size_t)4 * g.tab_bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+            CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+            D.um_Rb = uh.Rb;
+            D.um_r3 = uh.r3;
+            D.um_need = uh.need;
+        }
+    }
     return 0;
 }
 
@@ -643,8 +769,87 @@ int launch_otsu(const Pass& P, int l0, int nl, cudaStream_t st) {
     return 0;
 }
 
+template <int EPL>
+int launch_umma(dstr_ctx* ctx, const UmmaLevelArgs& ua, int grid, size_t smem, const DispatchParams& dp, cudaStream_t st) {
+    static std::mutex mtx;
+    static bool done[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        const int dev = ctx->device & 63;
+        if (!done[dev]) {
+            CK(ctx, cudaFuncSetAttribute(notch_umma_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            done[dev] = true;
+        }
+    }
+    notch_umma_kernel<EPL><<<grid, UM_THREADS, smem, st>>>(ua, ctx->d_pstat, dp);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Row filter of level l on the tensor cores; returns -1000 when the geometry does not qualify.
+int launch_filter_umma(const Pass& P, int l, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const LevelGeom& g = ctx->geom[l];
+    const TapTable& T = ctx->taps[l];
+    const UmmaGeom ug = umma_geom(g.W);
+    if (!ug.ok || !T.cfg[0].d_umma || !T.cfg[1].d_umma) return -1000;
+    if ((g.pitch % 4) != 0 || (g.pstride % 4) != 0) return -1000;
+    UmmaLevelArgs ua;
+    ua.cH = ctx->d_H[l];
+    ua.Hl = g.H;
+    ua.n = g.W;
+    ua.pitch = g.pitch;
+    ua.pstride = g.pstride;
+    ua.lstat = ctx->d_lstat + (size_t)(l - 1) * P.level_stride;
+    ua.stat_stride = P.stat_stride;
+    ua.nh = ug.nh;
+    ua.nout = ug.nout;
+    ua.P = ug.P;
+    ua.Nt = ug.Nt;
+    ua.NC = ug.NC;
+    ua.Kpad = ug.Kpad;
+    ua.items_per_plane = (g.H + UM_ROWS - 1) / UM_ROWS;
+    ua.rows_per_item = std::min(UM_ROWS, (((g.H + ua.items_per_plane - 1) / ua.items_per_plane) + 7) & ~7);
+    ua.items_per_plane = (g.H + ua.rows_per_item - 1) / ua.rows_per_item;
+    ua.n_items = ua.items_per_plane * P.z;
+    ua.tab_bytes = ug.tab_bytes;
+    ua.xs_stride = ug.xs_stride;
+    ua.mw = ug.mw;
+    ua.vec_ok = (reinterpret_cast<uintptr_t>(ua.cH) % 16 == 0) ? 1 : 0;
+    for (int c = 0; c < 2; ++c) {
+        ua.cfg[c].tables = T.cfg[c].d_umma;
+        ua.cfg[c].Rb = T.cfg[c].um_Rb;
+        ua.cfg[c].r3 = T.cfg[c].um_r3;
+        ua.cfg[c].need_band = T.cfg[c].um_need;
+    }
+    const int grid = std::min(ua.n_items, ctx->sm_count);
+    ua.scratch_stride = (size_t)4 * ug.NC * UM_CHUNK_BYTES;
+    const size_t need = ua.scratch_stride * (size_t)ctx->sm_count;
+    if (ctx->um_scratch_bytes[l] < need) {
+        // (re)allocation only happens on the first pass over a new geometry: drain everything first
+        CK(ctx, cudaDeviceSynchronize());
+        if (ctx->d_um_scratch[l]) cudaFree(ctx->d_um_scratch[l]);
+        ctx->d_um_scratch[l] = nullptr;
+        ctx->um_scratch_bytes[l] = 0;
+        CK(ctx, cudaMalloc(&ctx->d_um_scratch[l], need));
+        CK(ctx, cudaMemset(ctx->d_um_scratch[l], 0, need));  // rows / chunks never written must stay finite
+        ctx->um_scratch_bytes[l] = need;
+    }
+    ua.scratch = ctx->d_um_scratch[l];
+    const int epl = (g.W + 31) / 32;
+    if (epl <= 5) return launch_umma<5>(ctx, ua, grid, ug.smem, P.dp, st);
+    if (epl <= 9) return launch_umma<9>(ctx, ua, grid, ug.smem, P.dp, st);
+    if (epl <= 17) return launch_umma<17>(ctx, ua, grid, ug.smem, P.dp, st);
+    return launch_umma<33>(ctx, ua, grid, ug.smem, P.dp, st);
+}
+
 int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
     dstr_ctx* ctx = P.ctx;
+    if (ctx->use_umma) {
+        const int rcu = launch_filter_umma(P, l, st);
+        if (rcu != -1000) return rcu;
+    }
     const LevelGeom& g = ctx->geom[l];
     const TapTable& T = ctx->taps[l];
     FilterLevelArgs fa;
@@ -781,6 +986,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
     P.dp.mode = (mode == DSTR_MODE_DISPATCH) ? 1 : 0;
     ctx->last_levels = L;
     ctx->last_z = z;
+    ctx->last_dp = P.dp;
 
     ScopedTimer t_all(ctx, 7);
     if (L > 0) CK(ctx, cudaMemsetAsync(ctx->d_lstat, 0, sizeof(LevelStat) * P.level_stride * L, st));
@@ -1005,9 +1211,9 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         g.pstride = (size_t)g.H * g.pitch;
         ctx->geom[l] = g;
         // slack: the synthesis kernel reads columns m+1, m+2 unconditionally (8 floats), the row filter
-        // loads whole 32-lane groups of a row (up to 31 floats past the last row)
+        // loads whole 32-lane groups of a row for a templated element count (up to 32 x 65 floats past the last row start)
         CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * (g.pstride * max_planes + 8)));
-        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 64)));
+        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 2112)));  // 32 x 65 + 32
     }
     if (ctx->Lalloc > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lalloc * max_planes));
     CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));
@@ -1049,11 +1255,16 @@ int dstr_destroy(dstr_ctx* ctx) {
         if (ctx->d_A[l]) cudaFree(ctx->d_A[l]);
         if (ctx->d_H[l]) cudaFree(ctx->d_H[l]);
         for (int c = 0; c < 2; ++c)
-            if (ctx->taps[l].cfg[c].d_buf) cudaFree(ctx->taps[l].cfg[c].d_buf);
+        {
+                if (ctx->taps[l].cfg[c].d_buf) cudaFree(ctx->taps[l].cfg[c].d_buf);
+                if (ctx->taps[l].cfg[c].d_umma) cudaFree(ctx->taps[l].cfg[c].d_umma);
+            }
     }
     for (int l = 0; l < 2; ++l)
         for (int b2 = 0; b2 < 2; ++b2)
             if (ctx->d_pyr[l][b2]) cudaFree(ctx->d_pyr[l][b2]);
+    for (int l = 0; l <= kMaxLevels; ++l)
+        if (ctx->d_um_scratch[l]) cudaFree(ctx->d_um_scratch[l]);
     if (ctx->d_lstat) cudaFree(ctx->d_lstat);
     if (ctx->d_pstat) cudaFree(ctx->d_pstat);
     if (ctx->d_flat) cudaFree(ctx->d_flat);  // d_dark lives in the same allocation
@@ -1522,6 +1733,92 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
     return 0;
 }
 
+int dstr_set_umma(dstr_ctx* ctx, int enabled) {
+    if (!ctx) return DSTR_E_ARG;
+    ctx->use_umma = enabled != 0;
+    return 0;
+}
+
+int dstr_notch_umma_info(int n, int* info /*[8]*/) {
+    if (n <= 0 || !info) return DSTR_E_ARG;
+    const UmmaGeom g = umma_geom(n);
+    info[0] = g.ok ? 1 : 0;
+    info[1] = g.P;
+    info[2] = g.Nt;
+    info[3] = g.NC;
+    info[4] = g.tab_bytes;
+    info[5] = (int)g.smem;
+    info[6] = g.nout;
+    info[7] = g.Kpad;
+    return 0;
+}
+
+int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, double* y, int* info /*[3]: Rb, r3, MMAs*/) {
+    // y = B x evaluated on the host through the very data path of notch_umma_kernel: the fp16 hi / lo
+    // Hankel tables addressed like the UMMA descriptors do (block = (u0 + k0) / 8 + u_local / 8 + k / 8,
+    // shifted copy u_local % 8), pre-scaled fp16 hi / lo operands, the band / remainder product lists;
+    // accumulation in double.  Lets CPU tests check table layout, banding, scaling and the split.
+    if (n <= 0 || !(s > 0.0) || !x || !y) return DSTR_E_ARG;
+    const UmmaGeom g = umma_geom(n);
+    if (!g.ok) return DSTR_E_UNSUPPORTED;
+    UmmaHost uh;
+    build_umma_host(n, s, g, uh);
+    const size_t th = (size_t)g.tab_bytes / 2;
+    float scale = 1.0f;
+    if (thr > 0.0 && thr < 1e30) {
+        int e;
+        std::frexp((float)thr, &e);
+        scale = std::ldexp(1.0f, std::max(-24, std::min(14 - e, 40)));
+    }
+    std::vector<float> EH(g.Kpad, 0.f), EL(g.Kpad, 0.f), OH(g.Kpad, 0.f), OL(g.Kpad, 0.f);
+    for (int v = 0; v < n; ++v) {
+        const float xv = (float)x[v] * scale, xp = (float)x[(n - v) % n] * scale;
+        const float e = xv + xp, o = xv - xp;
+        EH[v] = half_value(half_bits(e));
+        EL[v] = half_value(half_bits(e - EH[v]));
+        OH[v] = half_value(half_bits(o));
+        OL[v] = half_value(half_bits(o - OH[v]));
+    }
+    const double inv = 1.0 / ((double)scale * (double)UM_TABLE_SCALE);
+    long long mmas = 0;
+    for (int p = 0; p < g.P; ++p) {
+        const int u0 = p * g.Nt;
+        for (int ul = 0; ul < g.Nt; ++ul) {
+            const int u = u0 + ul;
+            if (u >= g.nout) break;
+            double dE = 0.0, dO = 0.0;
+            for (int c = 0; c < g.NC; ++c) {
+                const bool band = um_band(u0, g.Nt, c, n, uh.Rb);
+                for (int j = 0; j < 2; ++j) {
+                    if (ul == 0) mmas += (uh.r3 ? 3 : 1) + (band ? (uh.r3 ? 3 : 6) : 0);
+                    for (int k = 0; k < 16; ++k) {
+                        const int v = UM_KC * c + 16 * j + k;
+                        const size_t blk = (size_t)((u0 + UM_KC * c + 16 * j) >> 3) + (ul >> 3) + (k >> 3);
+                        const size_t o = blk * 64 + (size_t)(ul & 7) * 8 + (k & 7);
+                        const double tbh = half_value(uh.tabs[o]), tbl = half_value(uh.tabs[th + o]);
+                        const double trh = half_value(uh.tabs[2 * th + o]), trl = half_value(uh.tabs[3 * th + o]);
+                        dE += (double)EH[v] * trh;
+                        if (uh.r3) dE += (double)EL[v] * trh + (double)EH[v] * trl;
+                        if (band) {
+                            if (!uh.r3) dE += (double)EH[v] * tbh + (double)EL[v] * tbh + (double)EH[v] * tbl;
+                            dO += (double)OH[v] * tbh + (double)OL[v] * tbh + (double)OH[v] * tbl;
+                        }
+                    }
+                }
+            }
+            const double E = dE * inv, O = dO * inv;
+            y[u] = E - O;
+            if (u >= 1 && 2 * u != n) y[n - u] = E + O;
+        }
+    }
+    if (info) {
+        info[0] = uh.Rb;
+        info[1] = uh.r3;
+        info[2] = (int)mmas;
+    }
+    return 0;
+}
+
 int dstr_set_pyramid_outputs(dstr_ctx* ctx, void* level1, void* level2) {
     if (!ctx) return DSTR_E_ARG;
     if (!level1 && level2) return fail(ctx, DSTR_E_ARG, "level 2 needs level 1");
@@ -1621,7 +1918,8 @@ int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_
             o[8 * z + 1] = fmx;
             o[8 * z + 2] = ls[z].otsu_raw;
             o[8 * z + 3] = ls[z].thr;
-            o[8 * z + 4] = 0.f;
+            // filtering.py:462 as the device evaluated it for this plane (plane_uses_cells)
+            o[8 * z + 4] = (ctx->last_dp.mode != 0 && fg > bg && fg > (double)ctx->last_dp.high_int) ? 1.f : 0.f;
             o[8 * z + 5] = (float)fg;
             o[8 * z + 6] = (float)bg;
             o[8 * z + 7] = (float)ls[z].otsu_bin;

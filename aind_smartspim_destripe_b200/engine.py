@@ -107,6 +107,9 @@ def load_library() -> C.CDLL:
             "dstr_set_subchunk": (C.c_int, [vp, C.c_int]),
             "dstr_set_overlap": (C.c_int, [vp, C.c_int]),
             "dstr_set_tma": (C.c_int, [vp, C.c_int]),
+            "dstr_set_umma": (C.c_int, [vp, C.c_int]),
+            "dstr_notch_umma_info": (C.c_int, [C.c_int, ip]),
+            "dstr_notch_umma_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp, ip]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
             "dstr_set_pyramid_outputs": (C.c_int, [vp, vp, vp]),
         }
@@ -124,7 +127,8 @@ EXPORTED_SYMBOLS = (
     "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
-    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_downscale2x dstr_set_pyramid_outputs"
+    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_set_umma dstr_notch_umma_info "
+    "dstr_notch_umma_apply_host dstr_downscale2x dstr_set_pyramid_outputs"
 ).split()
 
 
@@ -180,6 +184,30 @@ def notch_apply_host(x: np.ndarray, s: float, eps: float = 1e-6) -> np.ndarray:
     if rc:
         _raise(rc, None, "dstr_notch_apply_host")
     return y
+
+
+def notch_umma_info(n: int) -> dict:
+    """Geometry of the tensor-core row filter for a band of width ``n``."""
+    info = (C.c_int * 8)()
+    rc = load_library().dstr_notch_umma_info(int(n), info)
+    if rc:
+        _raise(rc, None, "dstr_notch_umma_info")
+    keys = ("eligible", "passes", "outputs_per_pass", "k_chunks", "table_bytes", "smem_bytes", "outputs", "k_padded")
+    return dict(zip(keys, [int(v) for v in info]))
+
+
+def notch_umma_apply_host(x: np.ndarray, s: float, thr: float):
+    """B x through the data path of the tensor-core kernel, evaluated on the host (test support)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    info = (C.c_int * 3)()
+    rc = load_library().dstr_notch_umma_apply_host(
+        x.size, float(s), float(thr), x.ctypes.data_as(dp), y.ctypes.data_as(dp), info
+    )
+    if rc:
+        _raise(rc, None, "dstr_notch_umma_apply_host")
+    return y, {"Rb": int(info[0]), "r3": int(info[1]), "mmas_per_item": int(info[2])}
 
 
 def foreground_threshold(threshold_mask: float = 0.3) -> float:
@@ -438,6 +466,10 @@ class DestripeEngine:
 
     def set_tma(self, enabled: bool):
         self._ck(self.lib.dstr_set_tma(self.ctx, 1 if enabled else 0), "dstr_set_tma")
+
+    def set_umma(self, enabled: bool):
+        """Row filter on the tcgen05 tensor-core kernel (default) or on the CUDA-core kernel."""
+        self._ck(self.lib.dstr_set_umma(self.ctx, 1 if enabled else 0), "dstr_set_umma")
 
     def set_overlap(self, enabled: bool):
         self._ck(self.lib.dstr_set_overlap(self.ctx, 1 if enabled else 0), "dstr_set_overlap")

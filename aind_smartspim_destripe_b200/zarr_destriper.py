@@ -165,6 +165,7 @@ def destripe_volume(
     queue_depth: int = 2,
     pyramid_outputs: Optional[Sequence] = None,
     io_threads: int = 4,
+    device_workers: int = 2,
 ):
     """Stream ``volume[z0:z1]`` (array-like ``(Z, H, W)``, uint16 or float32) through the GPU.
 
@@ -176,44 +177,64 @@ def destripe_volume(
 
     ``io_threads``: the reader and the writer each split a chunk into that many Z-ranges and move
     them concurrently (array slicing / Zarr decode releases the GIL), which is what the reference
-    spreads over ``co_cpus`` processes.
+    spreads over ``co_cpus`` processes.  Ranges written to a chunked sink (``output.chunks``) are cut
+    on its Z-chunk boundaries, so no two threads ever touch the same stored chunk.
+    ``device_workers``: engine contexts fed from the same queue (each call is synchronous in its own
+    host thread), so the upload / kernels / download of consecutive chunks overlap.
+
+    A failure in the reader, a device worker or the writer stops all of them and is re-raised here
+    (the reference's consumers would hang on ``join``, zarr_destriper.py:1171).
 
     Returns a timing dict: ``read_s`` (decode / host I/O), ``device_s`` (pinned H2D + kernels +
-    D2H inside the engine), ``write_s`` and ``wall_s``.
+    D2H inside the engine, summed over the workers), ``write_s`` and ``wall_s``.
     """
+    from concurrent.futures import ThreadPoolExecutor
+
     Z, H, W = volume.shape[-3:]
     z0, z1 = (0, Z) if z_range is None else z_range
-    eng = _eng.DestripeEngine(H, W, max_planes=min(chunk_planes, 16), device=_eng.default_device() if device is None else device)
     in_dtype = np.uint16 if np.dtype(volume.dtype) == np.uint16 else np.float32
     out_dtype = np.uint16 if shadow_correction is not None else np.float32
     n_pyr = 0 if pyramid_outputs is None else len(pyramid_outputs)
     if n_pyr:
         if out_dtype != np.uint16 or chunk_planes % 4 or z0 % 4 or n_pyr > 2:
             raise ValueError("pyramid_outputs need uint16 output, chunk_planes % 4 == 0 and an aligned slab")
-    n_buf = queue_depth + 1
-    pyr_bufs = [[_eng.PinnedBuffer((max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
-                 for k in range(n_pyr)] for _ in range(n_buf)]
-    in_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
-    out_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
-    free_in: "queue.Queue[int]" = queue.Queue()
-    free_out: "queue.Queue[int]" = queue.Queue()
-    for i in range(n_buf):
-        free_in.put(i)
-        free_out.put(i)
-    ready: "queue.Queue" = queue.Queue()
-    done: "queue.Queue" = queue.Queue()
-    times = dict(read_s=0.0, device_s=0.0, write_s=0.0)
+    device_workers = max(1, int(device_workers))
+    dev = _eng.default_device() if device is None else device
+    n_buf = queue_depth + device_workers
+    engines, in_bufs, out_bufs, pyr_bufs = [], [], [], []
+    rpool = wpool = None
+    stop = threading.Event()
     errors = []
+    errors_lock = threading.Lock()
 
-    from concurrent.futures import ThreadPoolExecutor
+    def _fail(exc):
+        with errors_lock:
+            errors.append(exc)
+        stop.set()
+
+    def _get(q):
+        """Blocking get that gives up when another stage failed."""
+        while True:
+            try:
+                return q.get(timeout=0.2)
+            except queue.Empty:
+                if stop.is_set():
+                    raise _Stopped()
 
     io_threads = max(1, int(io_threads))
-    rpool = ThreadPoolExecutor(io_threads)
-    wpool = ThreadPoolExecutor(io_threads)
+    sink_chunks = getattr(output, "chunks", None)
+    z_chunk = int(sink_chunks[-3]) if sink_chunks is not None and len(sink_chunks) >= 3 else 1
 
-    def _split(n):
+    def _split(a, n, align=1):
+        """Z-ranges [s0, s1) (relative to ``a``) cut at multiples of ``align`` in absolute Z."""
         step = max(1, (n + io_threads - 1) // io_threads)
-        return [(s0, min(s0 + step, n)) for s0 in range(0, n, step)]
+        if align > 1:
+            step = ((step + align - 1) // align) * align
+            first = min(n, (align - a % align) % align)  # leading partial stored chunk: one writer
+            cuts = ([0] if first else []) + list(range(first, n, step))
+        else:
+            cuts = list(range(0, n, step))
+        return [(c, min(nx, n)) for c, nx in zip(cuts, cuts[1:] + [n]) if c < n]
 
     def _read_part(i, a, s0, s1):
         in_bufs[i].array[s0:s1] = volume[a + s0 : a + s1]
@@ -222,81 +243,130 @@ def destripe_volume(
         res = out_bufs[j].array[s0:s1]
         output[a + s0 : a + s1] = res if out_dtype == np.uint16 else np.clip(res, 0, 65535)
 
+    free_in: "queue.Queue[int]" = queue.Queue()
+    free_out: "queue.Queue[int]" = queue.Queue()
+    ready: "queue.Queue" = queue.Queue()
+    done: "queue.Queue" = queue.Queue()
+    times = dict(read_s=0.0, device_s=0.0, write_s=0.0)
+    times_lock = threading.Lock()
+
     def reader():
         try:
             for a in range(z0, z1, chunk_planes):
                 b = min(a + chunk_planes, z1)
-                i = free_in.get()
+                i = _get(free_in)
                 t = time.perf_counter()
-                list(rpool.map(lambda r: _read_part(i, a, r[0], r[1]), _split(b - a)))
+                list(rpool.map(lambda r: _read_part(i, a, r[0], r[1]), _split(a, b - a)))
                 times["read_s"] += time.perf_counter() - t
                 ready.put((i, a, b))
-        except Exception as exc:  # pragma: no cover
-            errors.append(exc)
+        except _Stopped:
+            pass
+        except BaseException as exc:
+            _fail(exc)
         finally:
-            ready.put(None)
+            for _ in range(device_workers):
+                ready.put(None)
+
+    tile = dataset_name.replace(".zarr", "")
+
+    def device_worker(eng):
+        try:
+            while True:
+                item = _get(ready)
+                if item is None:
+                    return
+                i, a, b = item
+                j = _get(free_out)
+                t = time.perf_counter()
+                if n_pyr:
+                    eng.set_pyramid_outputs(pyr_bufs[j][0].array, pyr_bufs[j][1].array if n_pyr > 1 else None)
+                fl.filter_planes(
+                    in_bufs[i].array[: b - a],
+                    tile,
+                    no_cells_config,
+                    cells_config,
+                    shadow_correction,
+                    microscope_high_int,
+                    out=out_bufs[j].array[: b - a],
+                    engine=eng,
+                )
+                with times_lock:
+                    times["device_s"] += time.perf_counter() - t
+                free_in.put(i)
+                done.put((j, a, b))
+        except _Stopped:
+            pass
+        except BaseException as exc:
+            _fail(exc)
+        finally:
+            done.put(None)
 
     def writer():
         try:
-            while True:
-                item = done.get()
+            live = device_workers
+            while live:
+                item = _get(done)
                 if item is None:
-                    return
+                    live -= 1
+                    continue
                 j, a, b = item
                 t = time.perf_counter()
-                list(wpool.map(lambda r: _write_part(j, a, r[0], r[1]), _split(b - a)))
+                list(wpool.map(lambda r: _write_part(j, a, r[0], r[1]), _split(a, b - a, z_chunk)))
                 for k in range(n_pyr):
                     sh = k + 1
                     n_k = (b - a) >> sh
                     pyramid_outputs[k][(a >> sh) : (a >> sh) + n_k] = pyr_bufs[j][k].array[:n_k]
                 times["write_s"] += time.perf_counter() - t
                 free_out.put(j)
-        except Exception as exc:  # pragma: no cover
-            errors.append(exc)
+        except _Stopped:
+            pass
+        except BaseException as exc:
+            _fail(exc)
 
     t_wall = time.perf_counter()
-    rt = threading.Thread(target=reader, daemon=True)
-    wt = threading.Thread(target=writer, daemon=True)
-    rt.start()
-    wt.start()
-    tile = dataset_name.replace(".zarr", "")
+    threads = []
     try:
-        while True:
-            item = ready.get()
-            if item is None:
-                break
-            i, a, b = item
-            j = free_out.get()
-            t = time.perf_counter()
-            if n_pyr:
-                eng.set_pyramid_outputs(pyr_bufs[j][0].array, pyr_bufs[j][1].array if n_pyr > 1 else None)
-            fl.filter_planes(
-                in_bufs[i].array[: b - a],
-                tile,
-                no_cells_config,
-                cells_config,
-                shadow_correction,
-                microscope_high_int,
-                out=out_bufs[j].array[: b - a],
-                engine=eng,
-            )
-            times["device_s"] += time.perf_counter() - t
+        for _ in range(device_workers):
+            engines.append(_eng.DestripeEngine(H, W, max_planes=min(chunk_planes, 16), device=dev))
+        pyr_bufs = [[_eng.PinnedBuffer((max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
+                     for k in range(n_pyr)] for _ in range(n_buf)]
+        in_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
+        out_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
+        for i in range(n_buf):
             free_in.put(i)
-            done.put((j, a, b))
+            free_out.put(i)
+        rpool = ThreadPoolExecutor(io_threads)
+        wpool = ThreadPoolExecutor(io_threads)
+        threads = [threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)]
+        threads += [threading.Thread(target=device_worker, args=(e,), daemon=True) for e in engines]
+        for t in threads:
+            t.start()
+        # the writer ends when every device worker has ended; an error anywhere sets `stop`, and every
+        # blocking get polls it, so no stage can wait forever on a stage that died
+        for t in threads:
+            while t.is_alive():
+                t.join(timeout=0.5)
+    except BaseException as exc:  # KeyboardInterrupt included
+        _fail(exc)
+        for t in threads:
+            t.join(timeout=5.0)
     finally:
-        done.put(None)
-        rt.join()
-        wt.join()
         times["wall_s"] = time.perf_counter() - t_wall
-        rpool.shutdown(wait=True)
-        wpool.shutdown(wait=True)
+        for pool in (rpool, wpool):
+            if pool is not None:
+                pool.shutdown(wait=True)
         for pb in in_bufs + out_bufs + [p for ps in pyr_bufs for p in ps]:
             pb.free()
-        eng.close()
+        for e in engines:
+            e.close()
     if errors:
         raise errors[0]
     times["planes"] = z1 - z0
     return times
+
+
+class _Stopped(Exception):
+    """Raised inside a pipeline stage when another stage failed."""
 
 
 # ----------------------------------------------------------------------------------------------
@@ -397,6 +467,9 @@ class _PlanesView:
         self.arr, self.t, self.c = arr, t, c
         self.shape = tuple(arr.shape[2:])
         self.dtype = np.dtype(arr.dtype)
+        ch = getattr(arr, "chunks", None)
+        if ch is not None:
+            self.chunks = tuple(ch[2:])  # lets destripe_volume cut concurrent writes on stored-chunk boundaries
 
     def __getitem__(self, key):
         return np.asarray(self.arr[self.t, self.c, key])

@@ -18,6 +18,7 @@ import itertools
 import json
 import lzma
 import os
+import threading
 import shutil
 import zlib
 from concurrent.futures import ThreadPoolExecutor
@@ -173,7 +174,7 @@ class ZarrArray:
         p = self._chunk_path(idx)
         p.parent.mkdir(parents=True, exist_ok=True)
         data = self.codec.encode(np.ascontiguousarray(block, dtype=self.dtype).tobytes())
-        tmp = p.with_name(p.name + f".{os.getpid()}.tmp")
+        tmp = p.with_name(p.name + f".{os.getpid()}.{threading.get_ident()}.tmp")  # unique per writer thread
         tmp.write_bytes(data)
         os.replace(tmp, p)
 

@@ -75,6 +75,35 @@ def test_device_notch_tables_bound_the_truncation_error(n, s, eps):
         assert np.abs(y - ref).max() <= (2e-6 if eps > 0 else 1e-7) * np.abs(x).max()
 
 
+@pytest.mark.parametrize("n,s", [(1026, 64.125), (1026, 32.06), (1002, 64.16), (515, 32.19), (503, 32.24), (260, 16.25),
+                                 (254, 16.3), (132, 8.25), (129, 8.3), (100, 50.0), (640, 3.0)])
+def test_tensor_core_tables_reproduce_the_operator(n, s):
+    """The fp16 hi/lo Hankel tables, descriptor addressing, banding and pre-scaling of the tcgen05
+    row filter (host evaluation of exactly that data path) reproduce irfft(rfft(x) * g)."""
+    info = E.notch_umma_info(n)
+    assert info["eligible"] == 1 and info["smem_bytes"] <= 226 * 1024
+    assert info["passes"] * info["outputs_per_pass"] >= info["outputs"] and 2 * info["outputs_per_pass"] <= 512
+    g = fl.notch(n, s)
+    rng = np.random.default_rng(n)
+    for trial, thr in enumerate([0.7, 12.0, 3.0, 0.0004]):
+        x = rng.standard_normal(n)
+        if trial == 1:
+            x = np.cumsum(x) / 10.0
+        if trial == 2:
+            x = np.ones(n)
+        x = np.clip(x / np.abs(x).max(), -1, 1) * thr  # |x| <= thr like the in-painted background
+        ref = x - fftpack.irfft(fftpack.rfft(x) * g)
+        y, d = E.notch_umma_apply_host(x, s, thr)
+        assert np.abs(y - ref).max() <= 3e-6 * thr, (trial, d, np.abs(y - ref).max() / thr)
+
+
+def test_tensor_core_geometry_limits():
+    assert E.notch_umma_info(68)["eligible"] == 0      # tiny bands stay on the CUDA-core kernel
+    assert E.notch_umma_info(2050)["eligible"] == 0    # tables + ring do not fit in shared memory
+    i = E.notch_umma_info(1026)
+    assert (i["passes"], i["outputs_per_pass"], i["k_chunks"]) == (3, 176, 33)
+
+
 def test_hybrid_design_is_much_cheaper_than_dense_on_production_bands():
     for n, s in [(1026, 64.125), (1002, 64.16), (515, 32.19), (503, 32.24)]:
         d = E.notch_design(n, s, 1e-6)
