@@ -53,14 +53,13 @@ struct NotchDevice {
     NotchTables nt = {};
     // tcgen05 path (dstr_notch_umma.cuh): fp16 hi / lo Hankel tables [TBh | TBl | TRh | TRl]
     uint4* d_umma = nullptr;
-    int um_Rb = 0, um_r3 = 0;
-    unsigned long long um_need = 0;
+    UmmaCfg um = {};  // table geometry of this config (tables = d_umma)
 };
 
 // Geometry of the tcgen05 row filter for a band of width n (depends on n only).
 struct UmmaGeom {
-    int nh = 0, nout = 0, P = 0, Nt = 0, NC = 0, Kpad = 0, tab_bytes = 0, mw = 0, xs_stride = 0;
-    size_t smem = 0;
+    int nh = 0, nout = 0, P = 0, Nt = 0, NC = 0, Kpad = 0, tr_bytes = 0, mw = 0;
+    size_t smem_fixed = 0;  // ring + mask bits (the tables come on top, per config)
     bool ok = false;
 };
 
@@ -105,7 +104,9 @@ struct dstr_ctx {
     cudaEvent_t ev_an[kMaxLevels + 1] = {}, ev_flt[kMaxLevels + 1] = {};
     bool overlap = true;
     bool use_tma = true;  // level-1 analysis through the TMA-staged kernel when the plane shape allows
-    bool use_umma = true;  // row filter on tcgen05 where the band geometry allows (dstr_notch_umma.cuh)
+    // row filter on tcgen05 where the band geometry allows (dstr_notch_umma.cuh).  Off by default: measured on
+    // B200 it is 6-10 % slower than the CUDA-core kernel; DSTR_UMMA=1 or dstr_set_umma turn it on
+    bool use_umma = false;
     // per-CTA operand scratch of the tcgen05 row filter, one per level (the levels' filters run
     // concurrently on the side streams)
     uint8_t* d_um_scratch[kMaxLevels + 1] = {};
@@ -461,20 +462,20 @@ UmmaGeom umma_geom(int n) {
     UmmaGeom g;
     g.nh = n / 2;
     g.nout = g.nh + 1;
-    g.P = (g.nout + 255) / 256;
+    g.P = (g.nout + UM_NT_MAX - 1) / UM_NT_MAX;
     g.Nt = (((g.nout + g.P - 1) / g.P) + 15) & ~15;
     g.NC = (n + UM_KC - 1) / UM_KC;
     g.Kpad = UM_KC * g.NC;
     const int L = g.P * g.Nt + g.Kpad + 8;  // largest u + v (+ the 7 shifted copies)
-    g.tab_bytes = ((((L + 7) / 8) * 128) + 1023) & ~1023;
+    g.tr_bytes = ((L + 7) / 8) * 128;
     g.mw = g.NC;
-    g.xs_stride = g.Kpad + 4;  // = 4 (mod 32): the 8 rows of a 128-bit staging load hit 32 distinct banks
-    const size_t ring = (size_t)UM_STAGES * 4 * UM_CHUNK_BYTES;
-    g.smem = (size_t)4 * g.tab_bytes + ring + (size_t)UM_ROWS * g.mw * 4;
-    const size_t staging = (size_t)2 * UM_BATCH * g.xs_stride * 4;
-    g.ok = n >= 96 && n <= 32 * 33 && g.NC <= 64 && g.smem <= (size_t)226 * 1024 && staging <= ring && g.Nt <= 256;
+    g.smem_fixed = (size_t)UM_STAGES * 4 * UM_CHUNK_BYTES + (size_t)2 * UM_ROWS * g.mw * 4;
+    // (2n - Rb window of um_band: 1.5 n + 48 < 2 n - n / 2 always holds for n >= 96, so it never occurs)
+    g.ok = n >= 96 && n <= 32 * 33 && g.NC <= 64 && g.Nt <= UM_NT_MAX;
     return g;
 }
+
+constexpr size_t kUmmaSmemMax = 226 * 1024;  // 227 KB minus the kernel's static shared memory
 
 uint16_t half_bits(float v) {
     const __half h = __float2half_rn(v);
@@ -486,13 +487,15 @@ float half_value(uint16_t b) {
     return __half2float(__half(hr));
 }
 
-// Tables of one (band width n, notch width s): T[blk][r][e] = f(8 blk + r + e) for the periodic
-// sequences f = 256 * 1/2 hb restricted to circular distance <= Rb ("TB") and f = 256 * 1/2 (ha - that)
-// ("TR"; the full ha when the remainder needs the three-product split anyway), as fp16 hi and lo.
+// Tables of one (band width n, notch width s): core-matrix blocks T[blk][r][e] = f(8 blk + r + e) of the
+// periodic sequences f = 256 * 1/2 hb restricted to circular distance <= Rb ("TB") and
+// f = 256 * 1/2 (ha - that) ("TR"; the full ha when the remainder needs the three-product split anyway),
+// as fp16 hi and lo.  Layout [TRh | TRl (r3 only) | TBh | TBl]; TB is stored as the two windows of k the
+// band chunks touch when that is smaller (UmmaCfg, um_tb_off).
 struct UmmaHost {
-    std::vector<uint16_t> tabs;  // [TBh | TBl | TRh | TRl], tab_bytes / 2 halfs each
-    int Rb = 0, r3 = 0;
-    unsigned long long need = 0;
+    std::vector<uint16_t> tabs;
+    UmmaCfg cfg = {};
+    size_t bytes = 0;
 };
 
 void build_umma_host(int n, double s, const UmmaGeom& g, UmmaHost& out) {
@@ -521,30 +524,48 @@ void build_umma_host(int n, double s, const UmmaGeom& g, UmmaHost& out) {
         fr[k] = ha[k] - fb[k];
         r2 += fr[k] * fr[k];
     }
-    out.Rb = Rb;
-    out.r3 = std::sqrt(r2) > 0.004 ? 1 : 0;  // single-product error ~ |r|_2 2^-12 |x|
-    if (out.r3)
+    UmmaCfg& c = out.cfg;
+    c = UmmaCfg{};
+    c.Rb = Rb;
+    c.r3 = std::sqrt(r2) > 0.004 ? 1 : 0;  // single-product error ~ |r|_2 2^-12 |x|
+    if (c.r3)
         for (int k = 0; k < n; ++k) fr[k] = ha[k];  // E runs entirely on the split remainder table
-    const size_t th = (size_t)g.tab_bytes / 2;
-    out.tabs.assign(4 * th, 0);
-    const int nblk = g.tab_bytes / 128;
-    for (int blk = 0; blk < nblk; ++blk)
-        for (int r = 0; r < 8; ++r)
-            for (int e = 0; e < 8; ++e) {
-                const int k = (8 * blk + r + e) % n;
-                const size_t o = (size_t)blk * 64 + r * 8 + e;
-                const float vb = (float)(0.5 * fb[k] * (double)UM_TABLE_SCALE);
-                const float vr = (float)(0.5 * fr[k] * (double)UM_TABLE_SCALE);
-                const uint16_t bh = half_bits(vb), rh = half_bits(vr);
-                out.tabs[o] = bh;
-                out.tabs[th + o] = half_bits(vb - half_value(bh));
-                out.tabs[2 * th + o] = rh;
-                out.tabs[3 * th + o] = half_bits(vr - half_value(rh));
-            }
-    out.need = 0;
+    c.tr_bytes = g.tr_bytes;
+    // TB windows: a band chunk starting at k = lo reads k in [lo, lo + 16 + Nt + 22]
+    const int K0 = (Rb + g.Nt + 48 + 7) & ~7;
+    const int k1 = std::max(0, (n - Rb - g.Nt - 32)) & ~7;
+    const int len1 = ((n + Rb + g.Nt + 40 - k1) + 7) & ~7;
+    c.tb_compact = (K0 + len1) * 16 < g.tr_bytes ? 1 : 0;
+    c.tb_k1 = k1;
+    c.tb_w1_off = (K0 / 8) * 128;
+    c.tb_bytes = c.tb_compact ? ((K0 + len1) / 8) * 128 : g.tr_bytes;
+    const size_t total_bytes = (size_t)c.tr_bytes * (c.r3 ? 2 : 1) + (size_t)2 * c.tb_bytes;
+    out.bytes = (total_bytes + 15) & ~(size_t)15;
+    out.tabs.assign(out.bytes / 2, 0);
+    auto fill = [&](size_t off_hi_bytes, size_t off_lo_bytes, bool want_lo, int nblk, int kbase, const std::vector<double>& f) {
+        for (int blk = 0; blk < nblk; ++blk)
+            for (int r = 0; r < 8; ++r)
+                for (int e = 0; e < 8; ++e) {
+                    const int k = (kbase + 8 * blk + r + e) % n;
+                    const size_t o = (size_t)blk * 64 + r * 8 + e;
+                    const float v = (float)(0.5 * f[k] * (double)UM_TABLE_SCALE);
+                    const uint16_t h = half_bits(v);
+                    out.tabs[off_hi_bytes / 2 + o] = h;
+                    if (want_lo) out.tabs[off_lo_bytes / 2 + o] = half_bits(v - half_value(h));
+                }
+    };
+    const size_t oTRh = 0, oTRl = c.tr_bytes, oTBh = (size_t)c.tr_bytes * (c.r3 ? 2 : 1), oTBl = oTBh + c.tb_bytes;
+    fill(oTRh, oTRl, c.r3 != 0, c.tr_bytes / 128, 0, fr);
+    if (c.tb_compact) {
+        fill(oTBh, oTBl, true, K0 / 8, 0, fb);
+        fill(oTBh + c.tb_w1_off, oTBl + c.tb_w1_off, true, len1 / 8, k1, fb);
+    } else {
+        fill(oTBh, oTBl, true, c.tb_bytes / 128, 0, fb);
+    }
+    c.need_band = 0;
     for (int p = 0; p < g.P; ++p)
-        for (int c = 0; c < g.NC; ++c)
-            if (um_band(p * g.Nt, g.Nt, c, n, Rb)) out.need |= 1ull << c;
+        for (int cc = 0; cc < g.NC; ++cc)
+            if (um_band(p * g.Nt, g.Nt, cc, n, Rb)) c.need_band |= 1ull << cc;
 }
 
 int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
@@ -593,12 +614,13 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
         if (g.ok) {
             UmmaHost uh;
             build_umma_host(n, s, g, uh);
-            CK(ctx, cudaMalloc(&D.d_umma, (size_t)4 * g.tab_bytes));
-            CK(ctx, cudaMemcpyAsync(D.d_umma, uh.tabs.data(), (size_t)4 * g.tab_bytes, cudaMemcpyHostToDevice, ctx->s_comp));
-            CK(ctx, cudaStreamSynchronize(ctx->s_comp));
-            D.um_Rb = uh.Rb;
-            D.um_r3 = uh.r3;
-            D.um_need = uh.need;
+            if (g.smem_fixed + uh.bytes <= kUmmaSmemMax) {
+                CK(ctx, cudaMalloc(&D.d_umma, uh.bytes));
+                CK(ctx, cudaMemcpyAsync(D.d_umma, uh.tabs.data(), uh.bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+                CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+                D.um = uh.cfg;
+                D.um.tables = D.d_umma;
+            }
         }
     }
     return 0;
@@ -777,7 +799,7 @@ int launch_umma(dstr_ctx* ctx, const UmmaLevelArgs& ua, int grid, size_t smem, c
         std::lock_guard<std::mutex> lk(mtx);
         const int dev = ctx->device & 63;
         if (!done[dev]) {
-            CK(ctx, cudaFuncSetAttribute(notch_umma_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            CK(ctx, cudaFuncSetAttribute(notch_umma_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemMax));
             done[dev] = true;
         }
     }
@@ -813,19 +835,20 @@ int launch_filter_umma(const Pass& P, int l, cudaStream_t st) {
     ua.rows_per_item = std::min(UM_ROWS, (((g.H + ua.items_per_plane - 1) / ua.items_per_plane) + 7) & ~7);
     ua.items_per_plane = (g.H + ua.rows_per_item - 1) / ua.rows_per_item;
     ua.n_items = ua.items_per_plane * P.z;
-    ua.tab_bytes = ug.tab_bytes;
-    ua.xs_stride = ug.xs_stride;
     ua.mw = ug.mw;
     ua.vec_ok = (reinterpret_cast<uintptr_t>(ua.cH) % 16 == 0) ? 1 : 0;
+    size_t tab_max = 0;
     for (int c = 0; c < 2; ++c) {
-        ua.cfg[c].tables = T.cfg[c].d_umma;
-        ua.cfg[c].Rb = T.cfg[c].um_Rb;
-        ua.cfg[c].r3 = T.cfg[c].um_r3;
-        ua.cfg[c].need_band = T.cfg[c].um_need;
+        ua.cfg[c] = T.cfg[c].um;
+        const size_t tb = (size_t)ua.cfg[c].tr_bytes * (ua.cfg[c].r3 ? 2 : 1) + (size_t)2 * ua.cfg[c].tb_bytes;
+        tab_max = std::max(tab_max, (tb + 1023) & ~(size_t)1023);
     }
+    ua.tab_max = (int)tab_max;
+    const size_t smem = tab_max + ug.smem_fixed;
+    if (smem > kUmmaSmemMax) return -1000;
     const int grid = std::min(ua.n_items, ctx->sm_count);
     ua.scratch_stride = (size_t)4 * ug.NC * UM_CHUNK_BYTES;
-    const size_t need = ua.scratch_stride * (size_t)ctx->sm_count;
+    const size_t need = 2 * ua.scratch_stride * (size_t)ctx->sm_count;  // two item buffers per CTA
     if (ctx->um_scratch_bytes[l] < need) {
         // (re)allocation only happens on the first pass over a new geometry: drain everything first
         CK(ctx, cudaDeviceSynchronize());
@@ -837,11 +860,37 @@ int launch_filter_umma(const Pass& P, int l, cudaStream_t st) {
         ctx->um_scratch_bytes[l] = need;
     }
     ua.scratch = ctx->d_um_scratch[l];
+    ua.prof = nullptr;
+    static const bool um_prof = env_or("DSTR_UMMA_PROF", 0.0) != 0.0;
+    long long* d_prof = nullptr;
+    if (um_prof && l == 1) {
+        CK(ctx, cudaMalloc(&d_prof, sizeof(long long) * 256 * grid));
+        CK(ctx, cudaMemsetAsync(d_prof, 0, sizeof(long long) * 256 * grid, st));
+        ua.prof = d_prof;
+    }
     const int epl = (g.W + 31) / 32;
-    if (epl <= 5) return launch_umma<5>(ctx, ua, grid, ug.smem, P.dp, st);
-    if (epl <= 9) return launch_umma<9>(ctx, ua, grid, ug.smem, P.dp, st);
-    if (epl <= 17) return launch_umma<17>(ctx, ua, grid, ug.smem, P.dp, st);
-    return launch_umma<33>(ctx, ua, grid, ug.smem, P.dp, st);
+    int rc;
+    if (epl <= 5) rc = launch_umma<5>(ctx, ua, grid, smem, P.dp, st);
+    else if (epl <= 9) rc = launch_umma<9>(ctx, ua, grid, smem, P.dp, st);
+    else if (epl <= 17) rc = launch_umma<17>(ctx, ua, grid, smem, P.dp, st);
+    else rc = launch_umma<33>(ctx, ua, grid, smem, P.dp, st);
+    if (d_prof) {
+        // diagnostic build path (DSTR_UMMA_PROF=1): per-role wait / total cycles of the level-1 launch, CTA 0 and the mean
+        std::vector<long long> h((size_t)256 * grid);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        cudaFree(d_prof);
+        for (int w = 0; w < UM_THREADS / 32; ++w) {
+            const char* role = w == 0 ? "tma" : w == 1 ? "mma" : (w >= 4 && w < 8) ? "epi" : "prep";
+            if (w > 8 && w < UM_THREADS / 32 - 1) continue;  // the prep warps behave alike
+            double v[6] = {0, 0, 0, 0, 0, 0};
+            for (int b = 0; b < grid; ++b)
+                for (int k = 0; k < 6; ++k) v[k] += (double)h[((size_t)b * 32 + w) * 8 + k] / grid;
+            fprintf(stderr, "[umma prof L1] warp %2d %-4s wait %9.0f total %9.0f | pass1 %9.0f median %9.0f pass2 %9.0f | items %.1f\n",
+                    w, role, v[0], v[3], v[1], v[2], v[4], v[5]);
+        }
+    }
+    return rc;
 }
 
 int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
@@ -1238,6 +1287,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         CKC(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
     }
 #undef CKC
+    ctx->use_umma = env_or("DSTR_UMMA", 0.0) != 0.0;
     ctx->fg_half_thr = find_fg_half_threshold(0.3f);
     ctx->fg_thr32 = fg_threshold_f32(ctx->fg_half_thr);
     ctx->subchunk = 0;
@@ -1739,31 +1789,39 @@ int dstr_set_umma(dstr_ctx* ctx, int enabled) {
     return 0;
 }
 
-int dstr_notch_umma_info(int n, int* info /*[8]*/) {
+int dstr_notch_umma_info(int n, double s, int* info /*[8]*/) {
     if (n <= 0 || !info) return DSTR_E_ARG;
     const UmmaGeom g = umma_geom(n);
-    info[0] = g.ok ? 1 : 0;
+    size_t tab = 0;
+    if (g.ok && s > 0.0) {
+        UmmaHost uh;
+        build_umma_host(n, s, g, uh);
+        tab = (uh.bytes + 1023) & ~(size_t)1023;
+    }
+    info[0] = (g.ok && g.smem_fixed + tab <= kUmmaSmemMax) ? 1 : 0;
     info[1] = g.P;
     info[2] = g.Nt;
     info[3] = g.NC;
-    info[4] = g.tab_bytes;
-    info[5] = (int)g.smem;
+    info[4] = (int)tab;
+    info[5] = (int)(g.smem_fixed + tab);
     info[6] = g.nout;
     info[7] = g.Kpad;
     return 0;
 }
 
-int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, double* y, int* info /*[3]: Rb, r3, MMAs*/) {
+int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, double* y, int* info /*[4]*/) {
     // y = B x evaluated on the host through the very data path of notch_umma_kernel: the fp16 hi / lo
-    // Hankel tables addressed like the UMMA descriptors do (block = (u0 + k0) / 8 + u_local / 8 + k / 8,
-    // shifted copy u_local % 8), pre-scaled fp16 hi / lo operands, the band / remainder product lists;
-    // accumulation in double.  Lets CPU tests check table layout, banding, scaling and the split.
+    // Hankel tables addressed like the UMMA descriptors do (block of the k step + u_local / 8 + k / 8,
+    // shifted copy u_local % 8, compact band windows), pre-scaled fp16 hi / lo operands, the band /
+    // remainder product lists; accumulation in double.  Lets CPU tests check table layout, banding,
+    // scaling and the split.
     if (n <= 0 || !(s > 0.0) || !x || !y) return DSTR_E_ARG;
     const UmmaGeom g = umma_geom(n);
     if (!g.ok) return DSTR_E_UNSUPPORTED;
     UmmaHost uh;
     build_umma_host(n, s, g, uh);
-    const size_t th = (size_t)g.tab_bytes / 2;
+    const UmmaCfg& uc = uh.cfg;
+    const size_t oTRh = 0, oTRl = uc.tr_bytes, oTBh = (size_t)uc.tr_bytes * (uc.r3 ? 2 : 1), oTBl = oTBh + uc.tb_bytes;
     float scale = 1.0f;
     if (thr > 0.0 && thr < 1e30) {
         int e;
@@ -1779,6 +1837,11 @@ int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, dou
         OH[v] = half_value(half_bits(o));
         OL[v] = half_value(half_bits(o - OH[v]));
     }
+    auto tab = [&](size_t base_bytes, uint32_t blk_off_bytes, int ul, int k) {
+        // element (u_local, k) of the B operand whose descriptor starts at base + blk_off: SBO = LBO = 128 bytes
+        const size_t byte = base_bytes + blk_off_bytes + (size_t)((ul >> 3) + (k >> 3)) * 128 + (size_t)(ul & 7) * 16 + (size_t)(k & 7) * 2;
+        return (double)half_value(uh.tabs[byte / 2]);
+    };
     const double inv = 1.0 / ((double)scale * (double)UM_TABLE_SCALE);
     long long mmas = 0;
     for (int p = 0; p < g.P; ++p) {
@@ -1788,19 +1851,21 @@ int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, dou
             if (u >= g.nout) break;
             double dE = 0.0, dO = 0.0;
             for (int c = 0; c < g.NC; ++c) {
-                const bool band = um_band(u0, g.Nt, c, n, uh.Rb);
+                const bool band = um_band(u0, g.Nt, c, n, uc.Rb);
+                const int lo = u0 + UM_KC * c;
                 for (int j = 0; j < 2; ++j) {
-                    if (ul == 0) mmas += (uh.r3 ? 3 : 1) + (band ? (uh.r3 ? 3 : 6) : 0);
+                    if (ul == 0) mmas += (uc.r3 ? 3 : 1) + (band ? (uc.r3 ? 3 : 6) : 0);
+                    const int k0 = lo + 16 * j;
+                    const uint32_t roff = (uint32_t)(k0 >> 3) * 128u;
+                    const uint32_t boff = band ? um_tb_off(uc, lo, k0) : 0u;
                     for (int k = 0; k < 16; ++k) {
                         const int v = UM_KC * c + 16 * j + k;
-                        const size_t blk = (size_t)((u0 + UM_KC * c + 16 * j) >> 3) + (ul >> 3) + (k >> 3);
-                        const size_t o = blk * 64 + (size_t)(ul & 7) * 8 + (k & 7);
-                        const double tbh = half_value(uh.tabs[o]), tbl = half_value(uh.tabs[th + o]);
-                        const double trh = half_value(uh.tabs[2 * th + o]), trl = half_value(uh.tabs[3 * th + o]);
+                        const double trh = tab(oTRh, roff, ul, k);
                         dE += (double)EH[v] * trh;
-                        if (uh.r3) dE += (double)EL[v] * trh + (double)EH[v] * trl;
+                        if (uc.r3) dE += (double)EL[v] * trh + (double)EH[v] * tab(oTRl, roff, ul, k);
                         if (band) {
-                            if (!uh.r3) dE += (double)EH[v] * tbh + (double)EL[v] * tbh + (double)EH[v] * tbl;
+                            const double tbh = tab(oTBh, boff, ul, k), tbl = tab(oTBl, boff, ul, k);
+                            if (!uc.r3) dE += (double)EH[v] * tbh + (double)EL[v] * tbh + (double)EH[v] * tbl;
                             dO += (double)OH[v] * tbh + (double)OL[v] * tbh + (double)OH[v] * tbl;
                         }
                     }
@@ -1812,9 +1877,10 @@ int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, dou
         }
     }
     if (info) {
-        info[0] = uh.Rb;
-        info[1] = uh.r3;
+        info[0] = uc.Rb;
+        info[1] = uc.r3;
         info[2] = (int)mmas;
+        info[3] = uc.tb_compact;
     }
     return 0;
 }

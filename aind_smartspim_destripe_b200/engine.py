@@ -108,7 +108,7 @@ def load_library() -> C.CDLL:
             "dstr_set_overlap": (C.c_int, [vp, C.c_int]),
             "dstr_set_tma": (C.c_int, [vp, C.c_int]),
             "dstr_set_umma": (C.c_int, [vp, C.c_int]),
-            "dstr_notch_umma_info": (C.c_int, [C.c_int, ip]),
+            "dstr_notch_umma_info": (C.c_int, [C.c_int, C.c_double, ip]),
             "dstr_notch_umma_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp, ip]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
             "dstr_set_pyramid_outputs": (C.c_int, [vp, vp, vp]),
@@ -186,10 +186,10 @@ def notch_apply_host(x: np.ndarray, s: float, eps: float = 1e-6) -> np.ndarray:
     return y
 
 
-def notch_umma_info(n: int) -> dict:
-    """Geometry of the tensor-core row filter for a band of width ``n``."""
+def notch_umma_info(n: int, s: float = 0.0) -> dict:
+    """Geometry of the tensor-core row filter for a band of width ``n`` (tables sized for notch width ``s``)."""
     info = (C.c_int * 8)()
-    rc = load_library().dstr_notch_umma_info(int(n), info)
+    rc = load_library().dstr_notch_umma_info(int(n), float(s), info)
     if rc:
         _raise(rc, None, "dstr_notch_umma_info")
     keys = ("eligible", "passes", "outputs_per_pass", "k_chunks", "table_bytes", "smem_bytes", "outputs", "k_padded")
@@ -201,13 +201,13 @@ def notch_umma_apply_host(x: np.ndarray, s: float, thr: float):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.empty_like(x)
     dp = C.POINTER(C.c_double)
-    info = (C.c_int * 3)()
+    info = (C.c_int * 4)()
     rc = load_library().dstr_notch_umma_apply_host(
         x.size, float(s), float(thr), x.ctypes.data_as(dp), y.ctypes.data_as(dp), info
     )
     if rc:
         _raise(rc, None, "dstr_notch_umma_apply_host")
-    return y, {"Rb": int(info[0]), "r3": int(info[1]), "mmas_per_item": int(info[2])}
+    return y, {"Rb": int(info[0]), "r3": int(info[1]), "mmas_per_item": int(info[2]), "tb_compact": int(info[3])}
 
 
 def foreground_threshold(threshold_mask: float = 0.3) -> float:

@@ -65,6 +65,11 @@ def synthetic_plane(
     return np.clip(img, 0, 65535).astype(np.uint16)
 
 
+def _plane_job(job):
+    H, W, seed, kw = job
+    return synthetic_plane(H, W, seed=seed, **kw)
+
+
 def synthetic_stack(
     Z: int,
     H: int,
@@ -72,6 +77,7 @@ def synthetic_stack(
     base_seed: int = 0,
     cells_every: int = 0,
     n_unique: int = 0,
+    workers: int = 0,
     **plane_kwargs,
 ) -> np.ndarray:
     """(Z, H, W) uint16 stack.
@@ -82,12 +88,21 @@ def synthetic_stack(
     distinct planes and repeats them cyclically (large benchmark stacks).
     """
     n_gen = Z if n_unique <= 0 else min(Z, n_unique)
-    planes = []
+    jobs = []
     for z in range(n_gen):
         kw = dict(plane_kwargs)
         if cells_every > 0 and z % cells_every == cells_every - 1:
             kw.update(n_cells=max(kw.get("n_cells") or 0, (H * W) // 2000), cell_peak=30000.0)
-        planes.append(synthetic_plane(H, W, seed=base_seed + z, **kw))
+        jobs.append((H, W, base_seed + z, kw))
+    if workers and workers > 1 and n_gen >= 8:
+        # planes are independent and seeded individually: generate them in worker processes
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+
+        with ProcessPoolExecutor(max_workers=min(workers, n_gen), mp_context=mp.get_context("fork")) as ex:
+            planes = list(ex.map(_plane_job, jobs, chunksize=max(1, n_gen // (4 * workers))))
+    else:
+        planes = [_plane_job(j) for j in jobs]
     out = np.empty((Z, H, W), dtype=np.uint16)
     for z in range(Z):
         out[z] = planes[z % n_gen]

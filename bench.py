@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=2048)
     ap.add_argument("--width", type=int, default=2048)
     ap.add_argument("--batch-planes", type=int, default=0, help="planes per kernel launch (0 = engine default)")
-    ap.add_argument("--unique-planes", type=int, default=16)
+    ap.add_argument("--unique-planes", type=int, default=0, help="distinct synthetic planes in the chunk (0 = all planes distinct, seeds 0..Z-1)")
     ap.add_argument("--subchunk", type=int, default=0, help="planes per H2D/compute/D2H pipeline stage in the e2e leg (0 = engine default)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU-baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="issue every kernel on one stream in stage order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.c3 (dual-config) resident timing")
+    ap.add_argument("--no-umma", action="store_true", help="row filter on the CUDA-core kernel instead of the tcgen05 kernel")
     ap.add_argument("--e2e-sync", action="store_true", help="wait for every step's result before submitting the next")
     return ap.parse_args()
 
@@ -191,7 +193,7 @@ def cpu_reference_run(args, n_planes, cores, seed=1000):
     from oracle import worker as OW
 
     stack = S.synthetic_stack(n_planes, args.height, args.width, base_seed=seed,
-                              cells_every=2 if args.workload == "c3" else 0)
+                              cells_every=2 if args.workload == "c3" else 0, workers=cores)
     shadow = None
     cells = NO_CELLS
     if args.workload == "c3":
@@ -214,22 +216,28 @@ def run_reference(args):
     if rank != 0:
         return
     cores = OW.get_cpu_limit()
-    n_planes = args.cpu_planes or cores
+    # one step = the whole chunk of the workload (same config as the B200 arm); --cpu-planes bounds it
+    n_planes = args.cpu_planes or args.planes
     for _ in range(min(args.warmup, 1)):
         cpu_reference_run(args, max(1, cores // 2), cores)
     vals, times = [], []
     for k in range(args.steps):
-        v, dt = cpu_reference_run(args, n_planes, cores, seed=2000 + 100 * k)
+        v, dt = cpu_reference_run(args, n_planes, cores, seed=0)
         vals.append(v)
         times.append(dt)
     total_px = n_planes * args.height * args.width * args.steps
     value = total_px / sum(times) / 1e6
-    sample = f"{n_planes} planes of {args.height}x{args.width} per step on {cores} processes (bounded sample of the workload)"
+    sample = (f"{n_planes} planes of {args.height}x{args.width} per step on {cores} processes"
+              + ("" if n_planes == args.planes else " (bounded sample of the workload)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "CPU path; oracle port of the reference (pywt/skimage not installable)"},
+        "config": {"workload": workload_name(args), "planes_timed_per_step": n_planes,
+                   "note": "CPU path: numpy/scipy port of the reference (oracle/); pywt and skimage are installable neither "
+                           "here nor on the GPU box.  pywt's C DWT is about 2-3x faster than the port's numpy DWT on "
+                           "75-85 % of the time (SURVEY.md Appendix C): read the GPU/CPU ratio as an upper bound of "
+                           "roughly 2x on what the real stack would give."},
         "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -252,14 +260,17 @@ def run_b200(args):
     px_per_step = Z * H * W
 
     # ---- synthetic chunk (seeded; ranks get different planes) ---------------------------------
+    gen_workers = max(1, (os.cpu_count() or 8) // max(world, 1))
     stack = S.synthetic_stack(Z, H, W, base_seed=10_000 * rank, n_unique=args.unique_planes,
-                              cells_every=2 if args.workload == "c3" else 0)
+                              cells_every=2 if args.workload == "c3" else 0, workers=gen_workers)
     batch = args.batch_planes or min(Z, 128)
     eng = E.DestripeEngine(H, W, max_planes=batch, device=device)
     if args.no_overlap:
         eng.set_overlap(False)
     if args.no_tma:
         eng.set_tma(False)
+    if args.no_umma:
+        eng.set_umma(False)
     pn, pc = E.make_params(NO_CELLS), None
     mode, flags = E.MODE_LOGSPACE, 0
     if args.workload == "c3":
@@ -310,23 +321,96 @@ def run_b200(args):
     stage_ms, _ = eng.timers()
     eng.set_profiling(False)
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
-    # dominant single kernel launch: the level-1 row filter (filter_rows_kernel<33>); it sees the
-    # whole chunk once, so its algorithmic bytes per launch are 4 B x all pixels of the chunk
-    dom = "row_filter_level1"
-    if stage_ms.get(dom, 0.0) <= 0.0:  # fewer than one level (tiny planes): fall back to the largest stage
-        dom = max((k for k in stage_ms if k not in ("chunk_total", "row_filter_level1")), key=lambda k: stage_ms[k])
     peak, peak_src = measured_peak()
     algo_bytes = ALGO_BYTES_PER_PX * px_per_step
-    achieved = algo_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    step_ms = ms_total / args.steps
+    achieved = algo_bytes / (step_ms * 1e-3) / 1e9
+    # per-kernel entries: each stage against ITS OWN algorithmic bytes (what it has to read and write once),
+    # its device time (CUDA events on the compute stream, stage-ordered pass of the same steps) and, where an
+    # ncu capture is committed under profiles/, the measured DRAM bytes per launch group
+    lv = [(H, W)]
+    for l in range(1, eng.max_level + 1):
+        lv.append(E.level_shape(H, W, l))
+    band = [float(h * w) for h, w in lv]  # coefficients per plane and level (level 0 = pixels)
+    deep = sum(band[2:])
+    own_bytes = {
+        "analysis_l1": Z * (2.0 * band[0] + 8.0 * band[1]),                      # u16 in, cA1 + cH1 out
+        "analysis_deep": Z * (4.0 * sum(band[1:-1]) + 8.0 * deep),               # cA_{l-1} in, cA_l + cH_l out
+        "histogram": Z * 4.0 * sum(band[1:]),                                    # cH_l in
+        "row_filter": Z * 8.0 * sum(band[1:]),                                   # cH_l in, dH_l out
+        "row_filter_level1": Z * 8.0 * band[1],
+        "synthesis_deep": Z * (8.0 * deep + 4.0 * sum(band[1:-1])),              # dA_l + dH_l in, dA_{l-1} out
+        "final_synthesis_epilogue": Z * (8.0 * band[1] + 4.0 * band[0]),         # dA1 + dH1 + u16 in, u16 out
+    }
+    measured = recorded_traffic(args.workload)
+    if not isinstance(measured, dict):
+        measured = {}
+    kernels = []
+    for name, ob in own_bytes.items():
+        ms = stage_ms.get(name, 0.0)
+        if ms <= 0.0:
+            continue
+        gbs = ob / (ms * 1e-3) / 1e9
+        kernels.append({"stage": name, "ms": ms, "share_of_stage_sum": None, "algorithmic_bytes": ob, "achieved_GBps": gbs,
+                        "frac": gbs / peak, "dram_bytes_ncu": (measured.get("stages") or {}).get(name)})
+    ssum = sum(k["ms"] for k in kernels if k["stage"] != "row_filter_level1")
+    for k in kernels:
+        k["share_of_stage_sum"] = k["ms"] / ssum if ssum > 0 else None
+    dom = max((k for k in kernels if k["stage"] != "row_filter"), key=lambda k: k["ms"])["stage"] if kernels else None
     roofline = {
-        "bound": "hbm", "kernel": "filter_rows_kernel level 1" if dom == "row_filter_level1" else dom,
-        "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+        "bound": "hbm", "kernel": "whole pipeline (all kernels of one chunk pass)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": measured.get("dram_bytes_per_step"), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes,
-        "note": "CUDA-core bound stage (exact median + even/odd FIR + rank-J notch); frac is against the 4 B/px HBM bound",
-        "whole_pipeline_frac": (algo_bytes / (ms_total / args.steps * 1e-3) / 1e9) / peak,
+        "note": "headline = 4 B/px (u16 in + u16 out) x pixels of the chunk / device time of the whole step; kernels[] lists "
+                "every stage against its own algorithmic bytes; the stages are issue-slot bound (CUDA cores) or, for the "
+                "row filter, split between CUDA-core preparation and tcgen05 MMAs",
+        "dominant_stage": dom,
+        "row_filter_path": "cuda-core" if args.no_umma else "tcgen05 (kind::f16 hi/lo, TMEM accumulators)",
+        "kernels": kernels,
         "stage_ms_per_step": stage_ms,
     }
+
+    # ---- extra: the dual-config dispatch + dark/flat epilogue (BASELINE configs[2]) on the same engine ----
+    extra = None
+    if args.workload == "c2" and not args.no_extra:
+        stack3 = S.synthetic_stack(Z, H, W, base_seed=10_000 * rank + 5000, n_unique=args.unique_planes, cells_every=2,
+                                   workers=gen_workers)
+        flat, dark = S.synthetic_flat_dark(H, W)
+        eng.set_flat_dark(flat, dark.astype(np.float32))
+        d_in.upload(stack3)
+        pc3 = E.make_params(CELLS)
+
+        def step_c3(extra_flags=E.FLAG_NO_SYNC):
+            eng.filter_chunk_ptr(d_in.ptr, E.DSTR_U16, d_out.ptr, E.DSTR_U16, Z, pc3, pn, HIGH_INT, E.MODE_DISPATCH,
+                                 E.FLAG_SHADOW | extra_flags)
+
+        for _ in range(3):
+            step_c3()
+        eng.synchronize()
+        D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_c3()
+        e1.record(stream)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        ms3 = D.max_over_ranks(e0.elapsed_time(e1))
+        eng.set_profiling(True)
+        eng.reset_timers()
+        for _ in range(args.steps):
+            step_c3(0)
+        st3, _ = eng.timers()
+        eng.set_profiling(False)
+        v3 = world * px_per_step * args.steps / (ms3 * 1e-3) / 1e6
+        extra = {"c3": {"workload": "dual-config dispatch (cells sigma 64/thr 3, no_cells sigma 128/thr 12) + dark/flat epilogue, "
+                                    "every second plane with dense bright cells",
+                        "value": v3, "unit": "Mpixel/s", "ms_per_step": ms3 / args.steps,
+                        "whole_pipeline_frac": (algo_bytes / (ms3 / args.steps * 1e-3) / 1e9) / peak,
+                        "stage_ms_per_step": {k: v / args.steps for k, v in st3.items()}}}
+        d_in.upload(stack)
+        del stack3
 
     # ---- end to end through the public API with pinned host buffers ----------------------------
     e2e = None
@@ -361,8 +445,9 @@ def run_b200(args):
                "ms_per_step": 1e3 * dt / args.steps, "checksum": checksum,
                "submission": "synchronous" if args.e2e_sync else "asynchronous (DSTR_FLAG_NO_SYNC, 2 result buffers)"}
         # the ceiling of this figure: concurrent pinned H2D + D2H copies of the same buffers, nothing else
-        if rank == 0 and world == 1:
+        if True:  # every rank probes at the same time: the ceiling under the same contention as the e2e leg
             try:
+                D.barrier()
                 t_in = torch.from_numpy(pin_in.array.reshape(-1).view(np.uint8))
                 t_out = torch.from_numpy(pin_out.array.reshape(-1).view(np.uint8))
                 g_in = torch.empty(t_in.numel(), dtype=torch.uint8, device=f"cuda:{device}")
@@ -385,9 +470,13 @@ def run_b200(args):
                         both()
                     torch.cuda.synchronize()
                     gbps = max(gbps, 4 * t_in.numel() / (time.perf_counter() - tc) / 1e9)
-                e2e["pcie_bidirectional_GBps_each"] = gbps
-                e2e["pcie_ceiling_Mpixel_per_s"] = gbps * 1e9 / 2 / 1e6
+                gmin = -D.max_over_ranks(-gbps)
+                gsum = D.sum_over_ranks(gbps)
+                e2e["pcie_bidirectional_GBps_each"] = gmin
+                e2e["pcie_bidirectional_GBps_each_sum_over_ranks"] = gsum
+                e2e["pcie_ceiling_Mpixel_per_s"] = gsum * 1e9 / 2 / 1e6
                 e2e["frac_of_pcie_ceiling"] = e2e["value"] / e2e["pcie_ceiling_Mpixel_per_s"]
+                e2e["pcie_probe"] = f"concurrent pinned H2D + D2H of the e2e buffers on all {world} rank(s) at the same time"
                 del g_in, g_out
             except Exception as exc:  # the probe is informative only
                 e2e["pcie_probe_error"] = str(exc)
@@ -413,10 +502,11 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "planes_per_launch": batch,
+                       "distinct_planes": Z if args.unique_planes <= 0 else min(Z, args.unique_planes),
                        "l2_policy": "inputs (1.07 GB/chunk) larger than L2; no flush needed",
                        "sharding": f"one chunk per rank, {world} rank(s), no collective",
                        "numa_node_rank0": numa},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "extra": extra, "gpu_launches": int(launches),
             "clocks": clocks,
         }
         emit(line)

@@ -180,19 +180,22 @@ int dstr_set_overlap(dstr_ctx* ctx, int enabled);
 /* 1 (default): level-1 analysis through the TMA-staged kernel (cp.async.bulk ring + mbarrier) when
  * W >= 256 and rows are 16-byte multiples; 0: always the register-streaming kernel */
 int dstr_set_tma(dstr_ctx* ctx, int enabled);
-/* 1 (default): the row filter (filtering.py:195-217) of every band 96 <= W_l <= 1056 runs on the
- * 5th-generation tensor cores (tcgen05.mma kind::f16 on fp16 hi/lo operand pairs, accumulators in
- * TMEM, operands staged by TMA bulk copies; csrc/dstr_notch_umma.cuh); 0: always the CUDA-core kernel */
+/* 1: the row filter (filtering.py:195-217) of every band 96 <= W_l <= 1056 runs on the 5th-generation
+ * tensor cores (tcgen05.mma kind::f16 on fp16 hi/lo operand pairs, accumulators in TMEM, operands
+ * staged by TMA bulk copies; csrc/dstr_notch_umma.cuh); 0 (default, or environment DSTR_UMMA=1 to flip
+ * it): the CUDA-core kernel, which measures 6-10 % faster on B200.  Both paths
+ * pass the same parity tests. */
 int dstr_set_umma(dstr_ctx* ctx, int enabled);
 /* geometry of the tensor-core row filter for a band of width n:
- * info = {eligible, passes, outputs per pass, k chunks, table bytes, shared memory bytes, outputs, padded K} */
-int dstr_notch_umma_info(int n, int* info /*[8]*/);
+ * info = {eligible, passes, outputs per pass, k chunks, table bytes, shared memory bytes, outputs, padded K}
+ * (tables are sized for notch width s; s <= 0 reports the geometry only) */
+int dstr_notch_umma_info(int n, double s, int* info /*[8]*/);
 /* y = x - irfft(rfft(x) * notch(n, s)) (filtering.py:206-215) evaluated on the HOST through the data
  * path of the tensor-core kernel (fp16 hi/lo Hankel tables addressed like the UMMA descriptors, banded /
  * remainder product lists, power-of-two pre-scaling from `thr`), double accumulation; x has n entries
- * bounded by thr.  info = {band radius, three-product remainder flag, MMAs per 128-row item}.
- * Test support: no GPU needed. */
-int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, double* y, int* info /*[3]*/);
+ * bounded by thr.  info = {band radius, three-product remainder flag, MMAs per 128-row item, compact band
+ * tables}.  Test support: no GPU needed. */
+int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, double* y, int* info /*[4]*/);
 /* sub-chunk size (planes) used when streaming host buffers; 0 restores the default */
 int dstr_set_subchunk(dstr_ctx* ctx, int planes);
 

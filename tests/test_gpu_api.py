@@ -233,9 +233,10 @@ def test_batch_filter_directory_matches_oracle(tmp_path, production_configs, wit
     for p in names:
         img = np.asarray(D.imread(p))
         out = D.imread((dst / p.relative_to(src)).with_suffix(".tiff"))
-        ref = OF.filter_stripes(img.astype(np.float32), str(p), no_cells, cells, shadow, 2700)
+        # the reference feeds the file's uint16 planes (destriper.py:194): float64 flow (filtering.py:175)
+        ref = OF.filter_stripes(img, str(p), no_cells, cells, shadow, 2700)
         ref = np.clip(ref, 0, 65535).astype(np.uint16)
-        assert out.dtype == np.uint16 and out.shape == img.shape
+        assert img.dtype.kind == "u" and img.dtype.itemsize == 2 and out.dtype == np.uint16 and out.shape == img.shape
         frac, worst, _ = u16_agreement(out, ref)
         assert frac >= U16_FRACTION, (p.name, frac, worst)
 

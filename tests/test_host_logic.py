@@ -80,9 +80,9 @@ def test_device_notch_tables_bound_the_truncation_error(n, s, eps):
 def test_tensor_core_tables_reproduce_the_operator(n, s):
     """The fp16 hi/lo Hankel tables, descriptor addressing, banding and pre-scaling of the tcgen05
     row filter (host evaluation of exactly that data path) reproduce irfft(rfft(x) * g)."""
-    info = E.notch_umma_info(n)
+    info = E.notch_umma_info(n, s)
     assert info["eligible"] == 1 and info["smem_bytes"] <= 226 * 1024
-    assert info["passes"] * info["outputs_per_pass"] >= info["outputs"] and 2 * info["outputs_per_pass"] <= 512
+    assert info["passes"] * info["outputs_per_pass"] >= info["outputs"] and info["outputs_per_pass"] <= 128
     g = fl.notch(n, s)
     rng = np.random.default_rng(n)
     for trial, thr in enumerate([0.7, 12.0, 3.0, 0.0004]):
@@ -98,10 +98,11 @@ def test_tensor_core_tables_reproduce_the_operator(n, s):
 
 
 def test_tensor_core_geometry_limits():
-    assert E.notch_umma_info(68)["eligible"] == 0      # tiny bands stay on the CUDA-core kernel
-    assert E.notch_umma_info(2050)["eligible"] == 0    # tables + ring do not fit in shared memory
-    i = E.notch_umma_info(1026)
-    assert (i["passes"], i["outputs_per_pass"], i["k_chunks"]) == (3, 176, 33)
+    assert E.notch_umma_info(68, 4.0)["eligible"] == 0      # tiny bands stay on the CUDA-core kernel
+    assert E.notch_umma_info(2050, 128.0)["eligible"] == 0  # rows beyond 33 x 32 elements
+    i = E.notch_umma_info(1026, 64.125)
+    assert (i["passes"], i["outputs_per_pass"], i["k_chunks"]) == (5, 112, 33)
+    assert i["smem_bytes"] <= 200 * 1024
 
 
 def test_hybrid_design_is_much_cheaper_than_dense_on_production_bands():
