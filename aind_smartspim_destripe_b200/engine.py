@@ -111,6 +111,9 @@ def load_library() -> C.CDLL:
             "dstr_notch_umma_info": (C.c_int, [C.c_int, C.c_double, ip]),
             "dstr_notch_umma_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp, ip]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+            "dstr_blosc_available": (C.c_int, [C.c_int]),
+            "dstr_blosc_compress": (C.c_int64, [vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, vp, C.c_uint64]),
+            "dstr_blosc_decompress": (C.c_int64, [vp, C.c_uint64, vp, C.c_uint64]),
             "dstr_set_pyramid_outputs": (C.c_int, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
@@ -128,7 +131,8 @@ EXPORTED_SYMBOLS = (
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
     "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_set_umma dstr_notch_umma_info "
-    "dstr_notch_umma_apply_host dstr_downscale2x dstr_set_pyramid_outputs"
+    "dstr_notch_umma_apply_host dstr_downscale2x dstr_set_pyramid_outputs dstr_blosc_available dstr_blosc_compress "
+    "dstr_blosc_decompress"
 ).split()
 
 

@@ -5,7 +5,8 @@ The reference opens tiles and creates its outputs with ``zarr`` / ``ome_zarr`` /
 byte shuffle, ``dimension_separator="/"``).  None of those packages is installed here, so this
 module reads and writes the same on-disk format (``.zarray`` / ``.zgroup`` / ``.zattrs`` JSON, one
 file per chunk, C order, full-size edge chunks padded with ``fill_value``) with the codecs the
-standard library has (``null``, ``zlib``, ``bz2``, ``lzma``); any other compressor id (``blosc``)
+standard library has (``null``, ``zlib``, ``bz2``, ``lzma``) plus the reference's own ``blosc``
+(zstd / lz4 with byte shuffle: ``blosc1.py`` over the system ``libzstd`` / ``liblz4``); anything else
 is delegated to ``numcodecs`` when it can be imported and otherwise rejected by name.  Chunk
 decode / encode runs on a thread pool (the codecs release the GIL), which replaces the reference's
 ``co_cpus`` worker processes on the I/O side.
@@ -29,7 +30,7 @@ import numpy as np
 
 
 class _Codec:
-    def __init__(self, config: Optional[dict]):
+    def __init__(self, config: Optional[dict], itemsize: int = 1):
         self.config = config
         cid = None if config is None else config.get("id")
         self.id = cid
@@ -43,26 +44,40 @@ class _Codec:
             self.encode, self.decode = (lambda b: bz2.compress(b, level)), bz2.decompress
         elif cid == "lzma":
             self.encode, self.decode = lzma.compress, lzma.decompress
+        elif cid == "blosc" and _blosc_builtin_ok(config):
+            # the reference's codec (zarr_destriper.py:1066-1074): Blosc1 frames over the system libzstd / liblz4
+            from . import blosc1
+
+            cname = config.get("cname", "lz4")
+            clevel = int(config.get("clevel", 5))
+            shuffle = int(config.get("shuffle", 1))
+            if shuffle == -1:  # numcodecs AUTOSHUFFLE: byte shuffle unless the items are single bytes
+                shuffle = 1 if itemsize > 1 else 0
+            blocksize = int(config.get("blocksize", 0))
+            self.encode = lambda b: blosc1.compress(b, itemsize, clevel, shuffle, cname, blocksize)
+            self.decode = blosc1.decompress
         else:
             try:
                 import numcodecs  # noqa: WPS433
             except ImportError as exc:
                 raise NotImplementedError(
-                    f"zarr compressor {cid!r} needs numcodecs, which is not installed; "
-                    "supported without it: null, zlib, bz2, lzma"
+                    f"zarr compressor {config!r} needs numcodecs, which is not installed; supported without it: "
+                    "null, zlib, bz2, lzma, blosc (zstd / lz4, no or byte shuffle)"
                 ) from exc
             codec = numcodecs.get_codec(config)
             self.encode, self.decode = (lambda b: bytes(codec.encode(b))), (lambda b: bytes(codec.decode(b)))
 
 
-def default_compressor() -> Optional[dict]:
-    """blosc-zstd-3-shuffle like the reference when numcodecs is importable, else zlib level 1."""
-    try:
-        import numcodecs  # noqa: F401
+def _blosc_builtin_ok(config: dict) -> bool:
+    from . import blosc1
 
-        return {"id": "blosc", "cname": "zstd", "clevel": 3, "shuffle": 1, "blocksize": 0}
-    except ImportError:
-        return {"id": "zlib", "level": 1}
+    return config.get("cname", "lz4") in blosc1.COMPRESSOR_CODE and int(config.get("shuffle", 1)) in (0, 1, -1) \
+        and blosc1.available(config.get("cname", "lz4"))
+
+
+def default_compressor() -> Optional[dict]:
+    """The reference's output codec: blosc-zstd-3 with byte shuffle (zarr_destriper.py:1066-1074)."""
+    return {"id": "blosc", "cname": "zstd", "clevel": 3, "shuffle": 1, "blocksize": 0}
 
 
 def _norm_key(key, shape) -> Tuple[Tuple[slice, ...], Tuple[int, ...]]:
@@ -111,9 +126,10 @@ class ZarrArray:
         self.dtype = np.dtype(meta["dtype"])
         self.fill_value = meta.get("fill_value", 0) or 0
         self.sep = meta.get("dimension_separator", ".")
-        self.codec = _Codec(meta.get("compressor"))
+        self.codec = _Codec(meta.get("compressor"), self.dtype.itemsize)
         self.threads = max(1, int(threads))
         self._pool: Optional[ThreadPoolExecutor] = None
+        self._made_dirs = set()
 
     # ---- construction ---------------------------------------------------------------------
     @classmethod
@@ -143,7 +159,7 @@ class ZarrArray:
             "filters": None,
             "dimension_separator": dimension_separator,
         }
-        _Codec(compressor)  # fail before anything is written if the codec is unavailable
+        _Codec(compressor, np.dtype(dtype).itemsize)  # fail before anything is written if the codec is unavailable
         with open(path / ".zarray", "w") as fp:
             json.dump(meta, fp, indent=4)
         return cls(path, meta, "w", threads)
@@ -172,10 +188,14 @@ class ZarrArray:
         if block.shape != self.chunks:
             raise ValueError("write_chunk needs a full chunk")
         p = self._chunk_path(idx)
-        p.parent.mkdir(parents=True, exist_ok=True)
-        data = self.codec.encode(np.ascontiguousarray(block, dtype=self.dtype).tobytes())
+        if p.parent not in self._made_dirs:
+            p.parent.mkdir(parents=True, exist_ok=True)
+            self._made_dirs.add(p.parent)
+        block = np.ascontiguousarray(block, dtype=self.dtype)
+        data = self.codec.encode(block.reshape(-1).view(np.uint8).data)  # buffer protocol: no intermediate bytes copy
         tmp = p.with_name(p.name + f".{os.getpid()}.{threading.get_ident()}.tmp")  # unique per writer thread
-        tmp.write_bytes(data)
+        with open(tmp, "wb") as fp:
+            fp.write(data)
         os.replace(tmp, p)
 
     def _pool_map(self, fn, items):
@@ -232,11 +252,15 @@ class ZarrArray:
                 src.append(slice(lo - s.start, hi - s.start))
                 dst.append(slice(lo - i * c, hi - i * c))
                 full &= lo == i * c and hi == min((i + 1) * c, n)
-            if full:  # covers every stored element of the chunk: no read-modify-write
+            part = value[tuple(src)]
+            if full and part.shape == self.chunks:  # a whole interior chunk: encode the slice itself
+                self.write_chunk(idx, part)
+                return
+            if full:  # covers every stored element of an edge chunk: pad, no read-modify-write
                 block = np.full(self.chunks, self.fill_value, dtype=self.dtype)
             else:
                 block = self.read_chunk(idx).copy()
-            block[tuple(dst)] = value[tuple(src)]
+            block[tuple(dst)] = part
             self.write_chunk(idx, block)
 
         self._pool_map(store, self._chunk_ranges(sel))

@@ -196,6 +196,16 @@ int dstr_notch_umma_info(int n, double s, int* info /*[8]*/);
  * bounded by thr.  info = {band radius, three-product remainder flag, MMAs per 128-row item, compact band
  * tables}.  Test support: no GPU needed. */
 int dstr_notch_umma_apply_host(int n, double s, double thr, const double* x, double* y, int* info /*[4]*/);
+/* ---- Zarr chunk codec (next-row f1) ------------------------------------------------------------
+ * Blosc1 frames as the reference writes them (numcodecs Blosc(cname="zstd", clevel=3, shuffle=SHUFFLE),
+ * zarr_destriper.py:1066-1074): zstd (compressor 4) or lz4 (1) streams with optional byte shuffle, host
+ * code over the system libzstd / liblz4 (dlopen).  compress: dst_capacity >= nbytes + 16; returns the frame
+ * size.  decompress: returns the number of bytes written (dst == NULL: the size the frame expands to).
+ * Negative return = DSTR_E_*.  Thread safe; no GPU involved. */
+int dstr_blosc_available(int compressor);
+int64_t dstr_blosc_compress(const void* src, uint64_t nbytes, int typesize, int clevel, int shuffle, int compressor,
+                            uint64_t blocksize, void* dst, uint64_t dst_capacity);
+int64_t dstr_blosc_decompress(const void* frame, uint64_t frame_bytes, void* dst, uint64_t dst_capacity);
 /* sub-chunk size (planes) used when streaming host buffers; 0 restores the default */
 int dstr_set_subchunk(dstr_ctx* ctx, int planes);
 
