@@ -145,6 +145,7 @@ int64_t dstr_blosc_compress(const void* src_, uint64_t nbytes, int typesize, int
     size_t pos = kHeader + 4 * nblocks;
     int level = clevel >= 9 ? c.zstd_max_level() : (clevel == 8 ? c.zstd_max_level() - 2 : (2 * clevel - 1 < 1 ? 1 : 2 * clevel - 1));
     std::vector<uint8_t> tmp((flags & kShuffle) ? bs : 0);
+    std::vector<uint8_t> cbuf(compressor == 4 ? c.zstd_bound(bs) : (size_t)c.lz4_bound((int)bs));
     bool overflow = pos >= dst_capacity;
     for (size_t b = 0; b < nblocks && !overflow; ++b) {
         const size_t blen = (b + 1) * bs <= nbytes ? bs : nbytes - b * bs;
@@ -153,24 +154,23 @@ int64_t dstr_blosc_compress(const void* src_, uint64_t nbytes, int typesize, int
             shuffle(blk, tmp.data(), blen, ts);
             blk = tmp.data();
         }
-        if (pos + 4 + blen > dst_capacity) {  // room for the verbatim form at least
+        put32(dst + kHeader + 4 * b, (uint32_t)pos);
+        // the coder gets a full-size bound buffer (with less room zstd may give up although the result would fit)
+        size_t csize = 0;
+        if (compressor == 4) {
+            const size_t r = c.zstd_compress(cbuf.data(), cbuf.size(), blk, blen, level);
+            csize = c.zstd_is_error(r) ? 0 : r;
+        } else {
+            const int r = c.lz4_compress((const char*)blk, (char*)cbuf.data(), (int)blen, (int)cbuf.size());
+            csize = r > 0 ? (size_t)r : 0;
+        }
+        const bool verbatim = csize == 0 || csize >= blen;  // stored verbatim: csize == raw length
+        if (verbatim) csize = blen;
+        if (pos + 4 + csize > dst_capacity) {  // cannot beat a plain copy any more
             overflow = true;
             break;
         }
-        put32(dst + kHeader + 4 * b, (uint32_t)pos);
-        const size_t room = dst_capacity - pos - 4;
-        size_t csize = 0;
-        if (compressor == 4) {
-            const size_t r = c.zstd_compress(dst + pos + 4, room, blk, blen, level);
-            csize = c.zstd_is_error(r) ? 0 : r;  // "destination too small" = incompressible for our purposes
-        } else {
-            const int r = c.lz4_compress((const char*)blk, (char*)dst + pos + 4, (int)blen, (int)(room > 0x7fffffffu ? 0x7fffffff : room));
-            csize = r > 0 ? (size_t)r : 0;
-        }
-        if (csize == 0 || csize >= blen) {  // stored verbatim: csize == raw length
-            std::memcpy(dst + pos + 4, blk, blen);
-            csize = blen;
-        }
+        std::memcpy(dst + pos + 4, verbatim ? blk : cbuf.data(), csize);
         put32(dst + pos, (uint32_t)csize);
         pos += 4 + csize;
     }
