@@ -200,7 +200,7 @@ def destripe_volume(
             raise ValueError("pyramid_outputs need uint16 output, chunk_planes % 4 == 0 and an aligned slab")
     device_workers = max(1, int(device_workers))
     dev = _eng.default_device() if device is None else device
-    n_buf = queue_depth + device_workers
+    n_buf = max(2, queue_depth) + device_workers - 1
     engines, in_bufs, out_bufs, pyr_bufs = [], [], [], []
     rpool = wpool = None
     stop = threading.Event()
@@ -325,18 +325,27 @@ def destripe_volume(
 
     t_wall = time.perf_counter()
     threads = []
+    t_setup_end = t_stream_end = None
     try:
-        for _ in range(device_workers):
-            engines.append(_eng.DestripeEngine(H, W, max_planes=min(chunk_planes, 16), device=dev))
-        pyr_bufs = [[_eng.PinnedBuffer((max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
-                     for k in range(n_pyr)] for _ in range(n_buf)]
-        in_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
-        out_bufs = [_eng.PinnedBuffer((chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
+        # engine contexts and pinned buffers are created concurrently: page-locking GBs of host memory and the
+        # first CUDA context / module load each take seconds when done one after the other
+        with ThreadPoolExecutor(max(4, device_workers)) as setup:
+            f_eng = [setup.submit(_eng.DestripeEngine, H, W, min(chunk_planes, 16), dev) for _ in range(device_workers)]
+            f_in = [setup.submit(_eng.PinnedBuffer, (chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
+            f_out = [setup.submit(_eng.PinnedBuffer, (chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
+            f_pyr = [[setup.submit(_eng.PinnedBuffer, (max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
+                      for k in range(n_pyr)] for _ in range(n_buf)]
+            for f in f_eng:
+                engines.append(f.result())
+            in_bufs = [f.result() for f in f_in]
+            out_bufs = [f.result() for f in f_out]
+            pyr_bufs = [[f.result() for f in fs] for fs in f_pyr]
         for i in range(n_buf):
             free_in.put(i)
             free_out.put(i)
         rpool = ThreadPoolExecutor(io_threads)
         wpool = ThreadPoolExecutor(io_threads)
+        t_setup_end = time.perf_counter()
         threads = [threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)]
         threads += [threading.Thread(target=device_worker, args=(e,), daemon=True) for e in engines]
         for t in threads:
@@ -345,13 +354,13 @@ def destripe_volume(
         # blocking get polls it, so no stage can wait forever on a stage that died
         for t in threads:
             while t.is_alive():
-                t.join(timeout=0.5)
+                t.join(timeout=0.05)
+        t_stream_end = time.perf_counter()
     except BaseException as exc:  # KeyboardInterrupt included
         _fail(exc)
         for t in threads:
             t.join(timeout=5.0)
     finally:
-        times["wall_s"] = time.perf_counter() - t_wall
         for pool in (rpool, wpool):
             if pool is not None:
                 pool.shutdown(wait=True)
@@ -359,6 +368,13 @@ def destripe_volume(
             pb.free()
         for e in engines:
             e.close()
+        t_end = time.perf_counter()
+        times["wall_s"] = t_end - t_wall
+        if t_setup_end is not None and t_stream_end is not None:
+            # engine contexts + pinned buffers / the streaming pipeline itself / freeing them again
+            times["setup_s"] = t_setup_end - t_wall
+            times["stream_s"] = t_stream_end - t_setup_end
+            times["teardown_s"] = t_end - t_stream_end
     if errors:
         raise errors[0]
     times["planes"] = z1 - z0
@@ -577,7 +593,7 @@ def destripe_zarr(
         dist.barrier()  # rank 0 has created the arrays
     levels = [zs.ZarrArray.open(output_destriped_zarr / str(k), "w", threads) for k in range(n_levels)]
     z0, z1 = z_slab(Z, rank, world_size, align)
-    totals = dict(read_s=0.0, device_s=0.0, write_s=0.0, wall_s=0.0, planes=0)
+    totals = dict(read_s=0.0, device_s=0.0, write_s=0.0, wall_s=0.0, setup_s=0.0, stream_s=0.0, teardown_s=0.0, planes=0)
     for t in range(T):
         for c in range(C):
             pyr = [_PlanesView(levels[k], t, c) for k in range(1, n_levels)] if fused else None
@@ -586,7 +602,7 @@ def destripe_zarr(
                                      shadow, dataset_name=dataset_name, chunk_planes=chunk_planes, z_range=(z0, z1),
                                      pyramid_outputs=pyr, io_threads=1)
                 for k in totals:
-                    totals[k] += tm[k]
+                    totals[k] += tm.get(k, 0.0)
             if not fused and n_levels > 1 and z1 > z0:
                 # float output (no shadow correction) or unusual chunking: levels from the written data
                 a0 = z0 - z0 % 4
@@ -601,19 +617,38 @@ def destripe_zarr(
     return totals
 
 
+def tiles_of_rank(tiles: Sequence, rank: int, world_size: int, tile_parallel: Optional[bool] = None):
+    """Tiles a rank processes.  ``tile_parallel`` (default: as soon as there are at least as many tiles as
+    ranks): whole tiles are dealt round-robin to the ranks (BASELINE config 5: 8 tiles on 8 GPUs, SURVEY.md
+    section 8e); otherwise every rank takes part in every tile with its own Z-slab.  Returns (tiles, flag)."""
+    tiles = list(tiles)
+    if tile_parallel is None:
+        tile_parallel = world_size > 1 and len(tiles) >= world_size
+    if not tile_parallel or world_size <= 1:
+        return tiles, False
+    return [t for i, t in enumerate(tiles) if i % world_size == rank], True
+
+
 def destripe_channel(zarr_dataset_path, derivatives_path, channel_name, results_folder, xyz_resolution,
-                     estimated_channel_flats, laser_tiles, parameters):
+                     estimated_channel_flats, laser_tiles, parameters, tile_parallel: Optional[bool] = None):
     """Every ``*.zarr`` tile of a channel with the flat field of its laser side
-    (reference zarr_destriper.py:1214-1267)."""
+    (reference zarr_destriper.py:1214-1267, which loops the tiles sequentially :1231).
+
+    Under a multi-rank launch (``WORLD_SIZE`` / ``RANK``) the tiles are independent units of work: with
+    ``tile_parallel`` each rank destripes whole tiles on its own GPU (no collective, no shared chunk);
+    otherwise all ranks work on one tile at a time as Z-slabs."""
     from pathlib import Path
 
     from .destriper import imread
+    from .distributed import env_rank
 
+    rank, world_size, _ = env_rank()
     channel_dataset = Path(zarr_dataset_path) / channel_name
     destriped_data_folder = Path(results_folder) / "destriped_data"
     destriped_data_folder.mkdir(parents=True, exist_ok=True)
     timings = {}
-    for tile_path in sorted(channel_dataset.glob("*.zarr")):
+    mine, per_tile = tiles_of_rank(sorted(channel_dataset.glob("*.zarr")), rank, world_size, tile_parallel)
+    for tile_path in mine:
         output_folder = destriped_data_folder / channel_name / tile_path.name
         flatfield_path = None
         for side, tiles in laser_tiles.items():
@@ -627,5 +662,7 @@ def destripe_channel(zarr_dataset_path, derivatives_path, channel_name, results_
             dataset_path=tile_path, multiscale="0", output_destriped_zarr=output_folder,
             prediction_chunksize=(64, 1600, 2000), target_size_mb=3072, n_workers=0, batch_size=1,
             super_chunksize=(384, 1600, 2000), results_folder=results_folder, derivatives_path=derivatives_path,
-            xyz_resolution=xyz_resolution, parameters=parameters, flatfield=flatfield, lazy_callback_fn=None)
+            xyz_resolution=xyz_resolution, parameters=parameters, flatfield=flatfield, lazy_callback_fn=None,
+            # a rank that owns the whole tile runs it like a single-process job (no slab split, no barrier)
+            rank=0 if per_tile else None, world_size=1 if per_tile else None)
     return timings

@@ -38,7 +38,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--stream-planes", type=int, default=2000, help="planes of the streamed tile (c4 / c5)")
+    ap.add_argument("--pool-planes", type=int, default=64, help="distinct planes recycled through the streamed tile (c4 / c5)")
     ap.add_argument("--planes", type=int, default=128)
     ap.add_argument("--height", type=int, default=2048)
     ap.add_argument("--width", type=int, default=2048)
@@ -58,6 +60,11 @@ def parse_args():
 
 
 def workload_name(args):
+    if args.workload in ("c4", "c5"):
+        what = ("one SmartSPIM tile, Z-slab sharded over the ranks" if args.workload == "c4"
+                else "one tile per rank (multi-tile channel)")
+        return (f"{what}: {args.stream_planes}x1600x2000 uint16 streamed from host memory in 64-plane chunks through "
+                "destripe_volume (dual-config dispatch + dark/flat epilogue), H2D / kernels / D2H overlapped")
     kind = (
         "log-space filter (no_cells config: db3, level None, sigma 128, max_threshold 12)"
         if args.workload == "c2"
@@ -516,6 +523,96 @@ def run_b200(args):
     D.shutdown()
 
 
+class CyclicVolume:
+    """(Z, H, W) uint16 array-like that recycles a pool of distinct planes (a 2000-plane tile is 12.8 GB and
+    eight of them exceed the host memory: SURVEY.md section 8d)."""
+
+    def __init__(self, pool, Z):
+        self.pool, self.shape, self.dtype = pool, (Z,) + pool.shape[1:], pool.dtype
+
+    def __getitem__(self, key):
+        a, b, _ = key.indices(self.shape[0])
+        return self.pool[np.arange(a, b) % self.pool.shape[0]]
+
+
+class RecycledSink:
+    """(Z, H, W) sink: every result lands in a host ring (the write stage of the pipeline), a check-sum is kept."""
+
+    def __init__(self, shape, ring=128):
+        self.shape, self.ring, self.checksum = shape, np.zeros((ring,) + shape[1:], np.uint16), 0
+
+    def __setitem__(self, key, value):
+        a, b, _ = key.indices(self.shape[0])
+        for z0 in range(a, b, self.ring.shape[0]):
+            z1 = min(b, z0 + self.ring.shape[0])
+            self.ring[: z1 - z0] = value[z0 - a : z1 - a]
+        self.checksum += int(value[0, ::64, ::64].astype(np.int64).sum())
+
+
+def run_stream(args):
+    """c4 / c5: the streamed-tile configurations (BASELINE.json configs[3], configs[4]) through the public
+    chunk scheduler `zarr_destriper.destripe_volume` with host buffers on both sides."""
+    import torch
+
+    from aind_smartspim_destripe_b200 import distributed as D
+    from aind_smartspim_destripe_b200 import synthetic as S
+    from aind_smartspim_destripe_b200 import zarr_destriper as zd
+
+    rank, world, local = D.init()
+    device = local if world > 1 else int(os.environ.get("DSTR_DEVICE", "0"))
+    torch.cuda.set_device(device)
+    numa = None if args.no_numa_bind else D.bind_to_gpu_numa(device)
+    H, W, Z = 1600, 2000, args.stream_planes
+    pool = S.synthetic_stack(args.pool_planes, H, W, base_seed=20_000 + 1000 * rank, cells_every=2,
+                             workers=max(1, (os.cpu_count() or 8) // max(world, 1)))
+    flat, dark = S.synthetic_flat_dark(H, W)
+    shadow = dict(retrospective=True, flatfield=flat, darkfield=dark, tile_config=None)
+    if args.workload == "c4":
+        z0, z1 = zd.z_slab(Z, rank, world, 64)  # strong scaling: the tile is split
+    else:
+        z0, z1 = 0, Z  # weak scaling: a whole tile per rank
+    vol, sink = CyclicVolume(pool, Z), RecycledSink((Z, H, W))
+    sampler = ClockSampler(device)
+    steps_t, last = [], None
+    for k in range(max(args.warmup, 1) + args.steps):
+        timed = k >= max(args.warmup, 1)
+        D.barrier()
+        if timed and rank == 0 and not steps_t:
+            sampler.start()
+        t = zd.destripe_volume(vol, sink, NO_CELLS, CELLS, shadow, chunk_planes=64, z_range=(z0, z1), device=device,
+                               microscope_high_int=HIGH_INT, io_threads=max(2, 16 // max(world, 1)))
+        D.barrier()
+        if timed:
+            steps_t.append(D.max_over_ranks(t["stream_s"]))
+            last = t
+    clocks = sampler.stop() if rank == 0 else None
+    px_step = (Z if args.workload == "c4" else world * Z) * H * W
+    value = px_step * args.steps / sum(steps_t) / 1e6
+    split = {k: D.max_over_ranks(float(last[k])) for k in ("read_s", "device_s", "write_s", "setup_s", "stream_s", "teardown_s")}
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = ALGO_BYTES_PER_PX * value * 1e6 / 1e9
+        bytes_step = int(2 * px_step)
+        emit({
+            "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * sum(steps_t) / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "planes_per_chunk": 64, "distinct_planes": int(pool.shape[0]),
+                       "planes_per_rank": int(z1 - z0), "l2_policy": "streamed chunks (410 MB each) larger than L2",
+                       "sharding": ("Z-slabs aligned to the 64-plane output chunk" if args.workload == "c4" else "one tile per rank")
+                                   + f", {world} rank(s), no collective", "numa_node_rank0": numa},
+            "roofline": {"bound": "hbm", "kernel": "whole pipeline (streamed: bounded by the host <-> device copies)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * px_step},
+            "cpu_baseline": None,
+            "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": bytes_step,
+                    "note": "this workload IS the end-to-end path: host source -> pinned buffers -> GPU -> pinned buffers -> host sink"},
+            "stage_seconds_last_step_max_over_ranks": split,
+            "gpu_launches": None, "clocks": clocks,
+        })
+    D.shutdown()
+
+
 def main():
     args = parse_args()
     # Exactly one JSON line may reach stdout: libraries (e.g. the NCCL version banner) write to
@@ -526,6 +623,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("c4", "c5"):
+        run_stream(args)
     else:
         run_b200(args)
 

@@ -367,3 +367,64 @@ def test_asynchronous_host_chunks_match_synchronous_calls(production_configs):
     for b in pins + outs:
         b.free()
     eng.close()
+
+
+class _FailingSink:
+    """(Z, H, W) sink whose second write fails (disk full, codec error, ...)."""
+
+    def __init__(self, shape):
+        self.shape, self.calls = shape, 0
+
+    def __setitem__(self, key, value):
+        self.calls += 1
+        if self.calls >= 2:
+            raise OSError("sink failed")
+
+
+class _FailingSource:
+    def __init__(self, vol, fail_at):
+        self.vol, self.shape, self.dtype, self.fail_at = vol, vol.shape, vol.dtype, fail_at
+
+    def __getitem__(self, key):
+        if key.start >= self.fail_at:
+            raise OSError("source failed")
+        return self.vol[key]
+
+
+@pytest.mark.timeout(120)
+def test_destripe_volume_surfaces_stage_failures_instead_of_hanging(production_configs):
+    """A failing writer / reader / device stage stops the pipeline and re-raises (the reference's consumers
+    would hang on join, zarr_destriper.py:1171).  More chunks than buffers, so a dead stage would block the rest."""
+    no_cells, cells = production_configs
+    vol = S.synthetic_stack(40, 96, 128, base_seed=3)
+    with pytest.raises(OSError, match="sink failed"):
+        zd.destripe_volume(vol, _FailingSink(vol.shape), no_cells, cells, None, chunk_planes=4, queue_depth=2)
+    out = np.zeros(vol.shape, np.float32)
+    with pytest.raises(OSError, match="source failed"):
+        zd.destripe_volume(_FailingSource(vol, 20), out, no_cells, cells, None, chunk_planes=4, queue_depth=2)
+    with pytest.raises(KeyError):  # engine-side failure: tile missing from tile_config with per-side flats
+        flat = np.ones((96, 128), np.float32)
+        shadow = dict(retrospective=False, flatfield=[flat, flat], darkfield=np.zeros((96, 128), np.float32), tile_config={})
+        zd.destripe_volume(vol, np.zeros(vol.shape, np.uint16), no_cells, cells, shadow, dataset_name="0_0.zarr", chunk_planes=4)
+    # and a healthy run after the failures still works
+    good = np.zeros(vol.shape, np.float32)
+    t = zd.destripe_volume(vol, good, no_cells, cells, None, chunk_planes=8)
+    assert t["planes"] == 40 and np.all(good > 0)
+
+
+def test_destripe_volume_writes_are_cut_on_sink_chunk_boundaries(tmp_path, production_configs):
+    """io_threads > 1 with a chunked sink whose Z-chunk is deeper than a sub-range: no two writers may touch
+    the same stored chunk (lost updates / torn temp files otherwise)."""
+    from aind_smartspim_destripe_b200 import zarr_store as zs
+
+    no_cells, cells = production_configs
+    vol = S.synthetic_stack(48, 96, 128, base_seed=5)
+    flat, dark = S.synthetic_flat_dark(96, 128)
+    shadow = dict(retrospective=True, flatfield=flat, darkfield=dark, tile_config=None)
+    arr = zs.ZarrArray.create(tmp_path / "0", (1, 1) + vol.shape, (1, 1, 32, 64, 64), np.uint16, "default", "/")
+    sink = zd._PlanesView(arr, 0, 0)
+    assert sink.chunks == (32, 64, 64)
+    zd.destripe_volume(vol, sink, no_cells, cells, shadow, chunk_planes=24, io_threads=4, z_range=(8, 48))
+    ref = fl.filter_planes(vol[8:], "0_0", no_cells, cells, shadow, 2500)
+    np.testing.assert_array_equal(arr[0, 0, 8:], ref)
+    assert not list((tmp_path / "0").rglob("*.tmp"))

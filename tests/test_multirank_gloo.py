@@ -17,7 +17,7 @@ def _worker(rank, world, port, n_planes, out_dir):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     from aind_smartspim_destripe_b200 import distributed as D
-    from aind_smartspim_destripe_b200.zarr_destriper import z_slab
+    from aind_smartspim_destripe_b200.zarr_destriper import tiles_of_rank, z_slab
 
     r, w, local = D.init(backend="gloo")
     assert (r, w, local) == (rank, world, rank)
@@ -27,6 +27,14 @@ def _worker(rank, world, port, n_planes, out_dir):
     assert D.sum_over_ranks(float(z1 - z0)) == float(n_planes)
     # every rank "processes" only its slab of a shared volume (here: marks it)
     np.save(os.path.join(out_dir, f"slab_{rank}.npy"), np.array([z0, z1]))
+    # channel of 5 tiles: whole tiles dealt round-robin (BASELINE config 5), every tile owned exactly once
+    tiles = [f"tile_{i}.zarr" for i in range(5)]
+    mine, per_tile = tiles_of_rank(tiles, r, w)
+    assert per_tile and mine == tiles[r::w]
+    assert D.sum_over_ranks(float(len(mine))) == float(len(tiles))
+    # fewer tiles than ranks: all ranks share every tile as Z-slabs
+    assert tiles_of_rank(tiles[:1], r, w) == (tiles[:1], False)
+    assert tiles_of_rank(tiles, r, w, tile_parallel=False) == (tiles, False)
     D.barrier()
     D.shutdown()
 
