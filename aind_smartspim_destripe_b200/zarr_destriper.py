@@ -236,12 +236,25 @@ def destripe_volume(
             cuts = list(range(0, n, step))
         return [(c, min(nx, n)) for c, nx in zip(cuts, cuts[1:] + [n]) if c < n]
 
+    # optional zero-copy protocols: a source with ``read_into(dst, z0, z1)`` fills the pinned buffer itself (a
+    # decoder writing straight into it), a sink with ``write_from(src, z0, z1)`` consumes the pinned result
+    read_into = getattr(volume, "read_into", None)
+    write_from = getattr(output, "write_from", None)
+
     def _read_part(i, a, s0, s1):
-        in_bufs[i].array[s0:s1] = volume[a + s0 : a + s1]
+        if read_into is not None:
+            read_into(in_bufs[i].array[s0:s1], a + s0, a + s1)
+        else:
+            in_bufs[i].array[s0:s1] = volume[a + s0 : a + s1]
 
     def _write_part(j, a, s0, s1):
         res = out_bufs[j].array[s0:s1]
-        output[a + s0 : a + s1] = res if out_dtype == np.uint16 else np.clip(res, 0, 65535)
+        if out_dtype != np.uint16:
+            res = np.clip(res, 0, 65535)
+        if write_from is not None:
+            write_from(res, a + s0, a + s1)
+        else:
+            output[a + s0 : a + s1] = res
 
     free_in: "queue.Queue[int]" = queue.Queue()
     free_out: "queue.Queue[int]" = queue.Queue()

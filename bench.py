@@ -534,6 +534,14 @@ class CyclicVolume:
         a, b, _ = key.indices(self.shape[0])
         return self.pool[np.arange(a, b) % self.pool.shape[0]]
 
+    def read_into(self, dst, a, b):  # destripe_volume's zero-copy source protocol
+        P, z = self.pool.shape[0], a
+        while z < b:  # contiguous runs of the pool: plain memcpy
+            p0 = z % P
+            n = min(b - z, P - p0)
+            dst[z - a : z - a + n] = self.pool[p0 : p0 + n]
+            z += n
+
 
 class RecycledSink:
     """(Z, H, W) sink: every result lands in a host ring (the write stage of the pipeline), a check-sum is kept."""
@@ -547,6 +555,9 @@ class RecycledSink:
             z1 = min(b, z0 + self.ring.shape[0])
             self.ring[: z1 - z0] = value[z0 - a : z1 - a]
         self.checksum += int(value[0, ::64, ::64].astype(np.int64).sum())
+
+    def write_from(self, src, a, b):  # destripe_volume's zero-copy sink protocol
+        self[a:b] = src
 
 
 def run_stream(args):
