@@ -4,6 +4,7 @@
 // (/root/reference/code/aind_smartspim_destripe/zarr_destriper.py:797-906).
 #include "dstr_kernels.cuh"
 #include "dstr_notch_umma.cuh"
+#include "dstr_rows_mma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -54,6 +55,9 @@ struct NotchDevice {
     // tcgen05 path (dstr_notch_umma.cuh): fp16 hi / lo Hankel tables [TBh | TBl | TRh | TRl]
     uint4* d_umma = nullptr;
     UmmaCfg um = {};  // table geometry of this config (tables = d_umma)
+    // warp-level tensor path (dstr_rows_mma.cuh): one allocation [tr | T1f | T2f]
+    unsigned char* d_mma = nullptr;
+    MmaCfg mm = {};
 };
 
 // Geometry of the tcgen05 row filter for a band of width n (depends on n only).
@@ -107,6 +111,7 @@ struct dstr_ctx {
     // row filter on tcgen05 where the band geometry allows (dstr_notch_umma.cuh).  Off by default: measured on
     // B200 it is 6-10 % slower than the CUDA-core kernel; DSTR_UMMA=1 or dstr_set_umma turn it on
     bool use_umma = false;
+    int row_filter = 1;  // 0: FMA kernel (filter_rows_kernel), 1: mma.sync kernel (filter_rows_mma_kernel)
     // per-CTA operand scratch of the tcgen05 row filter, one per level (the levels' filters run
     // concurrently on the side streams)
     uint8_t* d_um_scratch[kMaxLevels + 1] = {};
@@ -568,6 +573,115 @@ void build_umma_host(int n, double s, const UmmaGeom& g, UmmaHost& out) {
             if (um_band(p * g.Nt, g.Nt, cc, n, Rb)) c.need_band |= 1ull << cc;
 }
 
+// ---- tables of the mma.sync row filter (dstr_rows_mma.cuh) from the hybrid design -------------
+struct MmaHost {
+    std::vector<uint16_t> tr;    // [E: hi0 | hi1 | lo0 | lo1][trlen_e], [O: ...][trlen_o]
+    std::vector<uint16_t> T1f;   // [nblk][Jpad / 16][32][16 halfs: 8 hi, 8 lo]
+    std::vector<uint16_t> T2f;   // [nseg16][Jpad / 16][32][16 halfs]
+    MmaCfg cfg = {};
+};
+
+void build_mma_host(int n, const NotchHost& h, MmaHost& out) {
+    const int nh = n / 2;
+    MmaCfg& c = out.cfg;
+    c = MmaCfg{};
+    auto pad16 = [](int v) { return (v + 15) & ~15; };
+    c.ntap_e = pad16(h.ntap_e);
+    c.ntap_o = pad16(h.ntap_o);
+    c.ue_lo = h.ue_lo;
+    c.uo_lo = h.uo_lo;
+    c.S_e = c.ntap_e / 16 + 1;
+    c.S_o = c.ntap_o / 16 + 1;
+    c.trlen_e = 16 * c.S_e + 32;
+    c.trlen_o = 16 * c.S_o + 32;
+    out.tr.assign((size_t)4 * (c.trlen_e + c.trlen_o), 0);
+    auto fill_tr = [&](size_t base, int trlen, int ntapP, const std::vector<float>& taps, int ntap) {
+        // tr[q] = taps[ntapP + 15 - q] (zero outside the real taps), scaled; copy 1 is shifted by one entry
+        std::vector<float> tr(trlen + 1, 0.f);
+        for (int q = 0; q <= trlen; ++q) {
+            const int kk = ntapP + 15 - q;
+            if (kk >= 0 && kk < ntap && kk < (int)taps.size()) tr[q] = taps[kk] * RM_TAP_SCALE;
+        }
+        for (int q = 0; q < trlen; ++q)
+            for (int sh = 0; sh < 2; ++sh) {
+                const float v = tr[q + sh];
+                const uint16_t hi = half_bits(v);
+                out.tr[base + (size_t)sh * trlen + q] = hi;
+                out.tr[base + (size_t)(2 + sh) * trlen + q] = half_bits(v - half_value(hi));
+            }
+    };
+    fill_tr(0, c.trlen_e, c.ntap_e, h.te, h.ntap_e);
+    fill_tr((size_t)4 * c.trlen_e, c.trlen_o, c.ntap_o, h.to, h.ntap_o);
+    c.J = h.J;
+    c.Jpad = pad16(h.J);
+    c.cs = 1.0f;
+    c.inv_x = 1.0f;
+    const int nseg16 = (nh + 1 + 15) / 16;
+    if (h.J > 0) {
+        const int OFFe = c.ue_lo + c.ntap_e;
+        c.blk_lo = OFFe >> 4;
+        const int blk_hi = (OFFe + nh + 1 + 15) >> 4;
+        c.nblk = blk_hi - c.blk_lo;
+        const int mtiles = c.Jpad / 16;
+        auto t1 = [&](int v, int j) -> float {  // omega_v cos(2 pi j v / n)
+            if (v < 0 || v > nh || j >= h.J) return 0.f;
+            return h.T1[(size_t)(v + 8) * h.Jpad + j];
+        };
+        const int nhp64 = ((((nh + 1 + 7) & ~7) + 63) & ~63);
+        auto t2 = [&](int j, int t) -> float {  // rho_j cos(2 pi j t / n), device layout of the CUDA-core kernel
+            if (t > nh || j >= h.J) return 0.f;
+            const int seg = t >> 3, k = t & 7;
+            const size_t off = (size_t)(seg >> 3) * 64 + (size_t)(k >> 2) * 32 + (size_t)(seg & 7) * 4 + (k & 3);
+            return h.T2[(size_t)j * nhp64 + off];
+        };
+        auto put = [](std::vector<uint16_t>& dst, size_t at, float v0, float v1) {  // one register: (hi pair) and, 8 halfs on, (lo pair)
+            const uint16_t h0 = half_bits(v0), h1 = half_bits(v1);
+            dst[at] = h0;
+            dst[at + 1] = h1;
+            dst[at + 8] = half_bits(v0 - half_value(h0));
+            dst[at + 9] = half_bits(v1 - half_value(h1));
+        };
+        out.T1f.assign((size_t)c.nblk * mtiles * 32 * 16, 0);
+        for (int blk = 0; blk < c.nblk; ++blk)
+            for (int mt = 0; mt < mtiles; ++mt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, tig = lane & 3;
+                    const int v0 = 16 * (c.blk_lo + blk) - OFFe;  // element of x_e at k = 0 of this block
+                    const size_t at = (((size_t)blk * mtiles + mt) * 32 + lane) * 16;
+                    // a0: (mode g, k 2tig..+1)  a1: (mode g + 8, k 2tig..+1)  a2: (mode g, k 2tig + 8..)  a3: (mode g + 8, k 2tig + 8..)
+                    const int m0 = 16 * mt + g, m1 = m0 + 8, k0 = v0 + 2 * tig;
+                    put(out.T1f, at + 0, t1(k0, m0), t1(k0 + 1, m0));
+                    put(out.T1f, at + 2, t1(k0, m1), t1(k0 + 1, m1));
+                    put(out.T1f, at + 4, t1(k0 + 8, m0), t1(k0 + 9, m0));
+                    put(out.T1f, at + 6, t1(k0 + 8, m1), t1(k0 + 9, m1));
+                }
+        // power-of-two scales: |c_j| <= 2 (nh + 1) 2^14 before scaling; T2 entries are tiny
+        int ce = 0;
+        std::frexp(2.0f * (float)(nh + 1), &ce);
+        c.cs = std::ldexp(1.0f, -ce);
+        float t2max = 0.f;
+        for (int j = 0; j < h.J; ++j)
+            for (int t = 0; t <= nh; ++t) t2max = std::max(t2max, std::fabs(t2(j, t)));
+        int te = 0;
+        std::frexp(std::max(t2max, 1e-30f), &te);
+        const float ts = std::ldexp(1.0f, 12 - te);  // largest entry in [2^11, 2^12)
+        c.inv_x = 1.0f / (c.cs * ts);
+        out.T2f.assign((size_t)nseg16 * mtiles * 32 * 16, 0);
+        for (int seg = 0; seg < nseg16; ++seg)
+            for (int kt = 0; kt < mtiles; ++kt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, tig = lane & 3;
+                    const size_t at = (((size_t)seg * mtiles + kt) * 32 + lane) * 16;
+                    const int tA = 16 * seg + g, tB = tA + 8, j0 = 16 * kt + 2 * tig;
+                    // A[m = output][k = mode]
+                    put(out.T2f, at + 0, t2(j0, tA) * ts, t2(j0 + 1, tA) * ts);
+                    put(out.T2f, at + 2, t2(j0, tB) * ts, t2(j0 + 1, tB) * ts);
+                    put(out.T2f, at + 4, t2(j0 + 8, tA) * ts, t2(j0 + 9, tA) * ts);
+                    put(out.T2f, at + 6, t2(j0 + 8, tB) * ts, t2(j0 + 9, tB) * ts);
+                }
+    }
+}
+
 int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     NotchDevice& D = ctx->taps[level].cfg[cfg];
     if (D.d_buf && D.sigma == sigma && D.eps == ctx->notch_eps) return 0;
@@ -605,6 +719,27 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
     D.nt.Jpad = hst.Jpad;
     D.sigma = sigma;
     D.eps = ctx->notch_eps;
+    {
+        MmaHost mh;
+        build_mma_host(n, hst, mh);
+        if (D.d_mma) {
+            cudaFree(D.d_mma);
+            D.d_mma = nullptr;
+        }
+        auto pad256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t b_tr = pad256(mh.tr.size() * 2), b_t1 = pad256(mh.T1f.size() * 2), b_t2 = pad256(mh.T2f.size() * 2);
+        CK(ctx, cudaMalloc(&D.d_mma, b_tr + b_t1 + b_t2 + 256));
+        CK(ctx, cudaMemcpyAsync(D.d_mma, mh.tr.data(), mh.tr.size() * 2, cudaMemcpyHostToDevice, ctx->s_comp));
+        if (!mh.T1f.empty())
+            CK(ctx, cudaMemcpyAsync(D.d_mma + b_tr, mh.T1f.data(), mh.T1f.size() * 2, cudaMemcpyHostToDevice, ctx->s_comp));
+        if (!mh.T2f.empty())
+            CK(ctx, cudaMemcpyAsync(D.d_mma + b_tr + b_t1, mh.T2f.data(), mh.T2f.size() * 2, cudaMemcpyHostToDevice, ctx->s_comp));
+        CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+        D.mm = mh.cfg;
+        D.mm.tr = reinterpret_cast<const __half*>(D.d_mma);
+        D.mm.T1f = reinterpret_cast<const uint4*>(D.d_mma + b_tr);
+        D.mm.T2f = reinterpret_cast<const uint4*>(D.d_mma + b_tr + b_t1);
+    }
     {
         const UmmaGeom g = umma_geom(n);
         if (D.d_umma) {
@@ -893,11 +1028,80 @@ int launch_filter_umma(const Pass& P, int l, cudaStream_t st) {
     return rc;
 }
 
+template <int EPL>
+int launch_rows_mma(dstr_ctx* ctx, const RowsMmaArgs& ra, int Z, size_t smem, const DispatchParams& dp, cudaStream_t st) {
+    static std::mutex mtx;
+    static bool done[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        const int dev = ctx->device & 63;
+        if (!done[dev]) {
+            CK(ctx, cudaFuncSetAttribute(filter_rows_mma_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            done[dev] = true;
+        }
+    }
+    dim3 grid((ra.Hl + FR_ROWS - 1) / FR_ROWS, Z);
+    filter_rows_mma_kernel<EPL><<<grid, FR_THREADS, smem, st>>>(ra, ctx->d_pstat, dp);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Row filter of level l with the contractions on mma.sync; returns -1000 when the band does not qualify.
+int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
+    dstr_ctx* ctx = P.ctx;
+    const LevelGeom& g = ctx->geom[l];
+    const TapTable& T = ctx->taps[l];
+    if (!T.cfg[0].d_mma || !T.cfg[1].d_mma || g.W < 16) return -1000;
+    RowsMmaArgs ra;
+    ra.cH = ctx->d_H[l];
+    ra.Hl = g.H;
+    ra.Wl = g.W;
+    ra.pitch = g.pitch;
+    ra.pstride = g.pstride;
+    ra.lstat = ctx->d_lstat + (size_t)(l - 1) * P.level_stride;
+    ra.stat_stride = P.stat_stride;
+    ra.cfg[0] = T.cfg[0].mm;
+    ra.cfg[1] = T.cfg[1].mm;
+    ra.nh = g.W / 2;
+    ra.nseg16 = (ra.nh + 1 + 15) / 16;
+    auto len_of = [&](int S) {  // entries the MMAs read, padded so that (len / 2) = 4 (mod 32): conflict-free operand loads
+        int len = 16 * ra.nseg16 + 16 * S;
+        len += (8 - len % 64 + 64) % 64;
+        return len;
+    };
+    ra.len_e = len_of(std::max(ra.cfg[0].S_e, ra.cfg[1].S_e));
+    ra.len_o = len_of(std::max(ra.cfg[0].S_o, ra.cfg[1].S_o));
+    ra.trlen_e_max = std::max(ra.cfg[0].trlen_e, ra.cfg[1].trlen_e);
+    ra.trlen_o_max = std::max(ra.cfg[0].trlen_o, ra.cfg[1].trlen_o);
+    ra.Jpad_max = std::max(ra.cfg[0].Jpad, ra.cfg[1].Jpad);
+    {
+        static const int pf = (int)env_or("DSTR_FILTER_PREFETCH", -1.0);
+        ra.prefetch_blocks = pf >= 0 ? pf : 8 * ctx->sm_count;
+        if ((g.pitch * 4) % 16 != 0) ra.prefetch_blocks = 0;
+    }
+    const int epl = (g.W + 31) / 32;
+    const size_t smem = 2 * ((size_t)4 * ra.trlen_e_max + 4 * ra.trlen_o_max + (size_t)FR_ROWS * 2 * (ra.len_e + ra.len_o)) +
+                        8 * (size_t)std::max(FR_ROWS * ra.Jpad_max, 4) + 2 * (size_t)FR_ROWS * 2 * (ra.Jpad_max + 8) +
+                        4 * (size_t)FR_ROWS * (epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65);
+    if (smem > 227 * 1024 || epl > 65) return -1000;
+    if (epl <= 2) return launch_rows_mma<2>(ctx, ra, P.z, smem, P.dp, st);
+    if (epl <= 5) return launch_rows_mma<5>(ctx, ra, P.z, smem, P.dp, st);
+    if (epl <= 9) return launch_rows_mma<9>(ctx, ra, P.z, smem, P.dp, st);
+    if (epl <= 17) return launch_rows_mma<17>(ctx, ra, P.z, smem, P.dp, st);
+    if (epl <= 33) return launch_rows_mma<33>(ctx, ra, P.z, smem, P.dp, st);
+    return launch_rows_mma<65>(ctx, ra, P.z, smem, P.dp, st);
+}
+
 int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
     dstr_ctx* ctx = P.ctx;
     if (ctx->use_umma) {
         const int rcu = launch_filter_umma(P, l, st);
         if (rcu != -1000) return rcu;
+    }
+    if (ctx->row_filter == 1) {
+        const int rcm = launch_filter_rows_mma(P, l, st);
+        if (rcm != -1000) return rcm;
     }
     const LevelGeom& g = ctx->geom[l];
     const TapTable& T = ctx->taps[l];
@@ -1288,6 +1492,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
     }
 #undef CKC
     ctx->use_umma = env_or("DSTR_UMMA", 0.0) != 0.0;
+    ctx->row_filter = (int)env_or("DSTR_ROW_FILTER", 1.0);
     ctx->fg_half_thr = find_fg_half_threshold(0.3f);
     ctx->fg_thr32 = fg_threshold_f32(ctx->fg_half_thr);
     ctx->subchunk = 0;
@@ -1308,6 +1513,7 @@ int dstr_destroy(dstr_ctx* ctx) {
         {
                 if (ctx->taps[l].cfg[c].d_buf) cudaFree(ctx->taps[l].cfg[c].d_buf);
                 if (ctx->taps[l].cfg[c].d_umma) cudaFree(ctx->taps[l].cfg[c].d_umma);
+                if (ctx->taps[l].cfg[c].d_mma) cudaFree(ctx->taps[l].cfg[c].d_mma);
             }
     }
     for (int l = 0; l < 2; ++l)
@@ -1780,6 +1986,12 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
         const int tm = n - t;
         if (t != 0 && tm != t) y[tm] = ye - yo;
     }
+    return 0;
+}
+
+int dstr_set_row_filter(dstr_ctx* ctx, int kind) {
+    if (!ctx || kind < 0 || kind > 1) return DSTR_E_ARG;
+    ctx->row_filter = kind;
     return 0;
 }
 

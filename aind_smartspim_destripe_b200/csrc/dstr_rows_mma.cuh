@@ -1,0 +1,406 @@
+// Row filter with the linear part on the warp-level tensor path (mma.sync m16n8k16, fp16 operand pairs).
+//
+// Same row arithmetic and the same operator design as filter_rows_kernel (dstr_kernels.cuh: mask, exact
+// median, in-painting; B x = A x_e + Bo x_o with compact even / odd FIRs `te` / `to` plus the rank-J cosine
+// correction), but every contraction runs as small matrix products instead of register-tiled FMA loops:
+//
+//   FIR       y[t0 + m] = sum_k A[m][k] * X[j0 + k],  A[m][k] = taps[m - k + const]  (a 16 x 16 Toeplitz tile,
+//             fragments read from a reversed tap table in shared memory), 16 outputs x 16 taps per MMA
+//   projection c[j] = sum_v T1[v][j] x_e[v]            (A = T1 tiles from global memory, fragment ordered)
+//   expansion  y_e[t] += sum_j c[j] T2[j][t]           (A = T2 tiles, B = c)
+//
+// The N = 8 columns of every product are the block's 4 rows x {hi, lo}: operands are fp16 pairs
+// x = hi + lo (power-of-two pre-scaling keeps them in range), so  A_hi * [X_hi | X_lo]  gives hi*hi and
+// hi*lo in one MMA and  A_lo * [X_hi | X_lo]  adds lo*hi (lo*lo is 2^-22 and harmless); the two columns
+// of a row are summed in the accumulator registers.  fp32 accumulation.  Thread (g, tig) of a warp ends
+// up with the outputs t0 + g and t0 + g + 8 of row tig.
+#pragma once
+#include "dstr_kernels.cuh"
+
+namespace dstr {
+
+struct MmaCfg {
+    const __half* tr;   // reversed tap tables [E: hi0 | hi1 | lo0 | lo1] (trlen_e each) then [O: ...] (trlen_o each)
+    const uint4* T1f;   // [nblk][Jpad / 16][32 lanes][hi, lo]  A fragments of T1 (modes x 16 elements)
+    const uint4* T2f;   // [nseg16][Jpad / 16][32 lanes][hi, lo] A fragments of T2 (16 outputs x 16 modes)
+    int ntap_e, ue_lo, ntap_o, uo_lo;  // tap counts padded to 16; tap k <-> circular offset u = u?_lo + k
+    int S_e, S_o;                      // k steps of the FIRs (ntap / 16 + 1)
+    int trlen_e, trlen_o;              // halfs per table copy
+    int J, Jpad;                       // Jpad: multiple of 16
+    int blk_lo, nblk;                  // 16-element blocks of the E index that hold x_e[0 .. nh]
+    float cs;                          // power-of-two scale applied to the c_j before the fp16 split
+    float inv_x;                       // 1 / (cs * T2 scale)
+};
+
+struct RowsMmaArgs {
+    float* cH;
+    int Hl, Wl, pitch;
+    size_t pstride;
+    const LevelStat* lstat;
+    int stat_stride;
+    MmaCfg cfg[2];  // [0] no_cells, [1] cells
+    int nh;         // n / 2: outputs t = 0 .. nh
+    int nseg16;     // 16-output segments
+    int len_e, len_o;  // halfs per (row, part) operand array (max over the configs; = 8 mod 64)
+    int trlen_e_max, trlen_o_max, Jpad_max;
+    int prefetch_blocks;
+};
+
+constexpr float RM_TAP_SCALE = 256.0f;
+#ifndef DSTR_RM_SG
+#define DSTR_RM_SG 4
+#endif
+constexpr int RM_SG = DSTR_RM_SG;  // 16-output segments a warp processes per tap-fragment load
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+#ifndef DSTR_RM_MINB
+#define DSTR_RM_MINB 8
+#endif
+template <int EPL>
+__global__ void __launch_bounds__(FR_THREADS, (EPL <= 33 ? DSTR_RM_MINB : 4))
+filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.Wl;
+    __half* s_tre = reinterpret_cast<__half*>(smem_raw);           // [4][trlen_e_max]
+    __half* s_tro = s_tre + 4 * a.trlen_e_max;                      // [4][trlen_o_max]
+    __half* s_E = s_tro + 4 * a.trlen_o_max;                        // [FR_ROWS * 2][len_e]
+    __half* s_O = s_E + FR_ROWS * 2 * a.len_e;                      // [FR_ROWS * 2][len_o]
+    unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * 2 * a.len_o);  // [FR_ROWS][Jpad_max]
+    const int chs = a.Jpad_max + 8;                                 // c operand stride: = 8 (mod 16) halfs
+    __half* s_ch = reinterpret_cast<__half*>(s_c64 + max(FR_ROWS * a.Jpad_max, 4));  // [FR_ROWS * 2][chs]
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_ch + FR_ROWS * 2 * chs);        // [FR_ROWS][EPL]
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int z = blockIdx.y;
+    const int row0 = blockIdx.x * FR_ROWS;
+    const int nrows = min(FR_ROWS, a.Hl - row0);
+    if (a.prefetch_blocks > 0 && lane == 0) {  // rows of the block that will run in this slot one wave later: DRAM -> L2
+        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_blocks;
+        const int pz = (int)(lin / gridDim.x);
+        const int prow = (int)(lin - (long long)pz * gridDim.x) * FR_ROWS + wid;
+        if (pz < (int)gridDim.y && prow < a.Hl) {
+            const float* pp = a.cH + (size_t)pz * a.pstride + (size_t)prow * a.pitch;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(a.pitch * 4) : "memory");
+        }
+    }
+    const int cfgi = plane_uses_cells(pstat[z], dp);
+    const MmaCfg mc = cfgi ? a.cfg[1] : a.cfg[0];
+    const LevelStat* st = a.lstat + (size_t)z * a.stat_stride;
+    const float thr_q = st->thr_q;
+    // power-of-two pre-scale: |x| <= thr, so the scaled operands stay below 2^15 (fp16 range)
+    float scale = 1.0f;
+    {
+        const float thr = st->thr;
+        if (thr > 0.f && thr < 1e30f) {
+            int e;
+            frexpf(thr, &e);
+            scale = ldexpf(1.0f, max(-24, min(14 - e, 40)));
+        }
+    }
+    const int nh = a.nh;
+
+    // tap tables of this plane's config -> shared memory
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(mc.tr);
+        unsigned* de = reinterpret_cast<unsigned*>(s_tre);
+        unsigned* dO = reinterpret_cast<unsigned*>(s_tro);
+        for (int c = 0; c < 4; ++c) {
+            for (int i = tid; i < mc.trlen_e / 2; i += FR_THREADS) de[c * (a.trlen_e_max / 2) + i] = src[c * (mc.trlen_e / 2) + i];
+            for (int i = tid; i < mc.trlen_o / 2; i += FR_THREADS)
+                dO[c * (a.trlen_o_max / 2) + i] = src[2 * mc.trlen_e + c * (mc.trlen_o / 2) + i];
+        }
+    }
+    for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS) s_c64[i] = 0ull;
+
+    const int OFFe = mc.ue_lo + mc.ntap_e, OFFo = mc.uo_lo + mc.ntap_o;
+    const int use_e = 16 * a.nseg16 + 16 * mc.S_e, use_o = 16 * a.nseg16 + 16 * mc.S_o;  // operand entries the MMAs read
+    if (wid < nrows) {
+        const float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
+        // ---- load, mask, keys (see filter_rows_kernel) --------------------------------------------
+        unsigned key[EPL];
+        {
+            const float* gl = grow + lane;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) key[i] = __float_as_uint(gl[32 * i]);
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const int e = lane + 32 * i;
+            const float c = __uint_as_float(key[i]);
+            key[i] = 0xffffffffu;
+            bool m = false;
+            if (e < n) {
+                m = __fmul_rn(c, c) > thr_q;
+                key[i] = f2key(m ? 0.0f : (c + 0.0f));
+            }
+            const unsigned mbits = __ballot_sync(0xffffffffu, m);
+            if (lane == 0) s_mask[wid * EPL + i] = mbits;
+        }
+        // ---- exact median of the zero-filled background (np.median, filtering.py:201) -------------
+        const unsigned KZ = 0x80000000u;
+        const int k1 = (n - 1) >> 1, k2 = n >> 1;
+        int cneg = 0, cle0 = 0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            cneg += (key[i] < KZ) ? 1 : 0;
+            cle0 += (key[i] <= KZ) ? 1 : 0;
+        }
+        cneg = __reduce_add_sync(0xffffffffu, cneg);
+        cle0 = __reduce_add_sync(0xffffffffu, cle0);
+        float med;
+        if (cneg <= k1 && k2 < cle0) {
+            med = 0.f;
+        } else {
+            unsigned res;
+            int lo_cnt, hi_cnt;
+            if (k1 < cneg) {
+                res = 0u;
+                lo_cnt = 0;
+                hi_cnt = cneg;
+            } else {
+                res = KZ;
+                lo_cnt = cneg;
+                hi_cnt = n;
+            }
+            bool unique = (hi_cnt - lo_cnt) == 1;
+            for (int b = 30; b >= 0 && !unique; --b) {
+                const unsigned trial = res | (1u << b);
+                int cnt = 0;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) cnt += (key[i] < trial) ? 1 : 0;
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (cnt <= k1) {
+                    res = trial;
+                    lo_cnt = cnt;
+                } else {
+                    hi_cnt = cnt;
+                }
+                unique = (hi_cnt - lo_cnt) == 1;
+            }
+            unsigned kk1 = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                if (key[i] >= res) kk1 = min(kk1, key[i]);
+            kk1 = __reduce_min_sync(0xffffffffu, kk1);
+            med = key2f(kk1);
+            if (k2 != k1) {
+                int cle = 0;
+                unsigned nxt = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    cle += (key[i] <= kk1) ? 1 : 0;
+                    if (key[i] > kk1) nxt = min(nxt, key[i]);
+                }
+                cle = __reduce_add_sync(0xffffffffu, cle);
+                nxt = __reduce_min_sync(0xffffffffu, nxt);
+                const unsigned kk2 = (cle >= k1 + 2) ? kk1 : nxt;
+                med = (key2f(kk1) + key2f(kk2)) * 0.5f;
+            }
+        }
+        // ---- in-painted row x = m ? med : c; circular even / odd parts, pre-scaled, as fp16 hi / lo:
+        //      E[tau + OFFe] = x_e[tau mod n] for every entry the MMAs read, same for O
+        {
+            __half* Eh = s_E + (wid * 2) * a.len_e;
+            __half* El = Eh + a.len_e;
+            __half* Oh = s_O + (wid * 2) * a.len_o;
+            __half* Ol = Oh + a.len_o;
+            const int tau_lo = -max(OFFe, OFFo);
+            const int tau_hi = max(use_e - OFFe, use_o - OFFo);
+            int t = (tau_lo + lane) % n;
+            if (t < 0) t += n;
+            const int step = 32 % n;
+            const float* gp = grow;
+            asm volatile("" : "+l"(gp));
+            const float hs = 0.5f * scale;
+            int ae = tau_lo + lane + OFFe, ao = tau_lo + lane + OFFo;
+            for (int tau = tau_lo + lane; tau < tau_hi; tau += 32, ae += 32, ao += 32) {
+                const unsigned tr = (t == 0) ? 0u : (unsigned)(n - t);
+                const float c1 = gp[(unsigned)t], c2 = gp[tr];
+                const float x1 = (__fmul_rn(c1, c1) > thr_q) ? med : c1;
+                const float x2 = (__fmul_rn(c2, c2) > thr_q) ? med : c2;
+                const float ve = hs * (x1 + x2), vo = hs * (x1 - x2);
+                if ((unsigned)ae < (unsigned)use_e) {
+                    const __half h = __float2half_rn(ve);
+                    Eh[ae] = h;
+                    El[ae] = __float2half_rn(ve - __half2float(h));
+                }
+                if ((unsigned)ao < (unsigned)use_o) {
+                    const __half h = __float2half_rn(vo);
+                    Oh[ao] = h;
+                    Ol[ao] = __float2half_rn(vo - __half2float(h));
+                }
+                t += step;
+                if (t >= n) t -= n;
+            }
+        }
+    }
+    __syncthreads();  // every row's operands are complete
+
+    const int g = lane >> 2, tig = lane & 3;
+    // ---- rank-J coefficients  c_j = sum_v T1[v][j] x_e[v]  (scaled like the operands) ------------
+    if (mc.J > 0) {
+        const int mtiles = mc.Jpad >> 4;
+        const int bw = (mc.nblk + FR_ROWS - 1) / FR_ROWS;
+        const int b_begin = wid * bw, b_end = min(mc.nblk, b_begin + bw);
+        const __half* xcol = s_E + g * a.len_e + 16 * mc.blk_lo + 2 * tig;  // column g = (row g >> 1, part g & 1)
+        for (int mt = 0; mt < mtiles; ++mt) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint4* tf = mc.T1f + ((size_t)b_begin * mtiles + mt) * 64 + 2 * lane;
+            for (int blk = b_begin; blk < b_end; ++blk) {
+                const uint4 fh = __ldg(tf), fl = __ldg(tf + 1);
+                const unsigned b0 = *reinterpret_cast<const unsigned*>(xcol + 16 * blk);
+                const unsigned b1 = *reinterpret_cast<const unsigned*>(xcol + 16 * blk + 8);
+                const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
+                mma_f16(acc, ah, b0, b1);
+                mma_f16(acc, al, b0, b1);
+                tf += (size_t)mtiles * 64;
+            }
+            // acc[0] + acc[1]: mode 16 mt + g of row tig (hi and lo operand columns); acc[2] + acc[3]: mode + 8.
+            // Partial sums of the warps are combined as 2^-24 fixed point (order-free integer adds: deterministic)
+            if (b_begin < b_end) {
+                atomicAdd(s_c64 + tig * a.Jpad_max + 16 * mt + g, (unsigned long long)__float2ll_rn((acc[0] + acc[1]) * 16777216.0f));
+                atomicAdd(s_c64 + tig * a.Jpad_max + 16 * mt + g + 8, (unsigned long long)__float2ll_rn((acc[2] + acc[3]) * 16777216.0f));
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < FR_ROWS * mc.Jpad; i += FR_THREADS) {
+            const int r = i / mc.Jpad, j = i - r * mc.Jpad;
+            const float c = __ll2float_rn((long long)s_c64[r * a.Jpad_max + j]) * (1.0f / 16777216.0f) * mc.cs;
+            const __half h = __float2half_rn(c);
+            s_ch[(2 * r) * chs + j] = h;
+            s_ch[(2 * r + 1) * chs + j] = __float2half_rn(c - __half2float(h));
+        }
+        __syncthreads();
+    }
+
+    // ---- FIRs + rank-J expansion + output ----------------------------------------------------------
+    // A warp takes groups of RM_SG consecutive 16-output segments.  The tap fragments of a k step are loaded once
+    // and used for every segment of the group (the shared-memory pipe, not the tensor pipe, is what limits this
+    // phase: 2 + 6 / RM_SG loads per pair of MMAs instead of 8).  The expansion runs first into the accumulator
+    // of the even part and is rescaled (a power of two) into the units of the FIR before the taps are added.
+    const float inv_f = 1.0f / (scale * RM_TAP_SCALE);
+    const float x_to_f = mc.inv_x * RM_TAP_SCALE;  // (1 / (cs ts)) / (1 / 256)
+    // q = 16 s + 2 tig - g + 15 indexes the reversed tap table; lanes with an odd q read the copy shifted by one
+    const int q0 = 2 * tig - g + 15;
+    const int odd = q0 & 1;
+    const __half* teh = s_tre + (odd ? a.trlen_e_max : 0) - odd + q0;
+    const __half* tel = s_tre + (odd ? 3 : 2) * a.trlen_e_max - odd + q0;
+    const __half* toh = s_tro + (odd ? a.trlen_o_max : 0) - odd + q0;
+    const __half* tol = s_tro + (odd ? 3 : 2) * a.trlen_o_max - odd + q0;
+    const int r = tig;  // the row whose outputs this thread ends up with
+    const bool rvalid = r < nrows;
+    float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + (rvalid ? r : 0)) * a.pitch;
+    const unsigned* mrow = s_mask + (rvalid ? r : 0) * EPL;
+    const __half* ecol = s_E + g * a.len_e + 2 * tig;  // operand column g = (row g >> 1, part g & 1)
+    const __half* ocol = s_O + g * a.len_o + 2 * tig;
+    // every warp owns a contiguous range of segments (sizes differ by at most one)
+    const int seg_lo = (a.nseg16 * wid) / FR_ROWS, seg_hi = (a.nseg16 * (wid + 1)) / FR_ROWS;
+    for (int sg0 = seg_lo; sg0 < seg_hi; sg0 += RM_SG) {
+        const int cnt = min(RM_SG, seg_hi - sg0);
+        float acc[RM_SG][4];
+        float ye[RM_SG][2];
+#pragma unroll
+        for (int i = 0; i < RM_SG; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        if (mc.J > 0) {
+            const int ktiles = mc.Jpad >> 4;
+            const __half* ccol = s_ch + g * chs + 2 * tig;
+            for (int kt = 0; kt < ktiles; ++kt) {
+                const unsigned b0 = *reinterpret_cast<const unsigned*>(ccol + 16 * kt);
+                const unsigned b1 = *reinterpret_cast<const unsigned*>(ccol + 16 * kt + 8);
+#pragma unroll
+                for (int i = 0; i < RM_SG; ++i) {
+                    const int seg = sg0 + i;
+                    if (i < cnt) {
+                        const uint4* tf = mc.T2f + ((size_t)seg * ktiles + kt) * 64 + 2 * lane;
+                        const uint4 fh = __ldg(tf), fl = __ldg(tf + 1);
+                        const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
+                        mma_f16(acc[i], ah, b0, b1);
+                        mma_f16(acc[i], al, b0, b1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RM_SG; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[i][k] *= x_to_f;
+        }
+        for (int s = 0; s < mc.S_e; ++s) {
+            unsigned ah[4], al[4];
+            ah[0] = *reinterpret_cast<const unsigned*>(teh + 16 * s);
+            ah[1] = *reinterpret_cast<const unsigned*>(teh + 16 * s - 8);
+            ah[2] = *reinterpret_cast<const unsigned*>(teh + 16 * s + 8);
+            ah[3] = ah[0];
+            al[0] = *reinterpret_cast<const unsigned*>(tel + 16 * s);
+            al[1] = *reinterpret_cast<const unsigned*>(tel + 16 * s - 8);
+            al[2] = *reinterpret_cast<const unsigned*>(tel + 16 * s + 8);
+            al[3] = al[0];
+#pragma unroll
+            for (int i = 0; i < RM_SG; ++i) {
+                const int seg = sg0 + i;
+                if (i < cnt) {
+                    const __half* xc = ecol + 16 * (seg + s);
+                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
+                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
+                    mma_f16(acc[i], ah, b0, b1);
+                    mma_f16(acc[i], al, b0, b1);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RM_SG; ++i) {
+            ye[i][0] = acc[i][0] + acc[i][1];
+            ye[i][1] = acc[i][2] + acc[i][3];
+            acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        }
+        for (int s = 0; s < mc.S_o; ++s) {
+            unsigned ah[4], al[4];
+            ah[0] = *reinterpret_cast<const unsigned*>(toh + 16 * s);
+            ah[1] = *reinterpret_cast<const unsigned*>(toh + 16 * s - 8);
+            ah[2] = *reinterpret_cast<const unsigned*>(toh + 16 * s + 8);
+            ah[3] = ah[0];
+            al[0] = *reinterpret_cast<const unsigned*>(tol + 16 * s);
+            al[1] = *reinterpret_cast<const unsigned*>(tol + 16 * s - 8);
+            al[2] = *reinterpret_cast<const unsigned*>(tol + 16 * s + 8);
+            al[3] = al[0];
+#pragma unroll
+            for (int i = 0; i < RM_SG; ++i) {
+                const int seg = sg0 + i;
+                if (i < cnt) {
+                    const __half* xc = ocol + 16 * (seg + s);
+                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
+                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
+                    mma_f16(acc[i], ah, b0, b1);
+                    mma_f16(acc[i], al, b0, b1);
+                }
+            }
+        }
+        if (!rvalid) continue;
+        // dH[t] = masked ? 0 : -(B x)[t];  (B x)[t] = y_e + y_o,  (B x)[n - t] = y_e - y_o
+#pragma unroll
+        for (int i = 0; i < RM_SG; ++i) {
+            if (i >= cnt) break;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = 16 * (sg0 + i) + g + 8 * h;
+                if (t > nh) continue;
+                const float yev = ye[i][h] * inv_f;
+                const float yo = (acc[i][2 * h] + acc[i][2 * h + 1]) * inv_f;
+                const bool md = (mrow[t >> 5] >> (t & 31)) & 1u;
+                orow[t] = md ? 0.f : -(yev + yo);
+                const int tm = n - t;
+                if (t >= 1 && tm != t) {
+                    const bool mm = (mrow[tm >> 5] >> (tm & 31)) & 1u;
+                    orow[tm] = mm ? 0.f : -(yev - yo);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dstr

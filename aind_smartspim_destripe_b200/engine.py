@@ -108,6 +108,7 @@ def load_library() -> C.CDLL:
             "dstr_set_overlap": (C.c_int, [vp, C.c_int]),
             "dstr_set_tma": (C.c_int, [vp, C.c_int]),
             "dstr_set_umma": (C.c_int, [vp, C.c_int]),
+            "dstr_set_row_filter": (C.c_int, [vp, C.c_int]),
             "dstr_notch_umma_info": (C.c_int, [C.c_int, C.c_double, ip]),
             "dstr_notch_umma_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp, ip]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -130,7 +131,7 @@ EXPORTED_SYMBOLS = (
     "dstr_notch_kernels dstr_notch_design dstr_notch_apply_host dstr_set_notch_tolerance dstr_host_alloc dstr_host_free dstr_host_register dstr_host_unregister "
     "dstr_device_alloc dstr_device_free dstr_memcpy_h2d dstr_memcpy_d2h dstr_synchronize "
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
-    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_set_umma dstr_notch_umma_info "
+    "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_set_umma dstr_set_row_filter dstr_notch_umma_info "
     "dstr_notch_umma_apply_host dstr_downscale2x dstr_set_pyramid_outputs dstr_blosc_available dstr_blosc_compress "
     "dstr_blosc_decompress"
 ).split()
@@ -474,6 +475,10 @@ class DestripeEngine:
     def set_umma(self, enabled: bool):
         """Row filter on the tcgen05 tensor-core kernel (default) or on the CUDA-core kernel."""
         self._ck(self.lib.dstr_set_umma(self.ctx, 1 if enabled else 0), "dstr_set_umma")
+
+    def set_row_filter(self, kind: int):
+        """0: register-tiled FMA row filter, 1 (default): mma.sync row filter."""
+        self._ck(self.lib.dstr_set_row_filter(self.ctx, int(kind)), "dstr_set_row_filter")
 
     def set_overlap(self, enabled: bool):
         self._ck(self.lib.dstr_set_overlap(self.ctx, 1 if enabled else 0), "dstr_set_overlap")

@@ -54,7 +54,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.c3 (dual-config) resident timing")
-    ap.add_argument("--no-umma", action="store_true", help="row filter on the CUDA-core kernel instead of the tcgen05 kernel")
+    ap.add_argument("--umma", action="store_true", help="row filter on the tcgen05 kernel (opt-in: measured slower)")
+    ap.add_argument("--row-filter", type=int, default=-1, help="0: FMA row filter, 1: mma.sync row filter (default: engine default)")
     ap.add_argument("--e2e-sync", action="store_true", help="wait for every step's result before submitting the next")
     return ap.parse_args()
 
@@ -276,8 +277,10 @@ def run_b200(args):
         eng.set_overlap(False)
     if args.no_tma:
         eng.set_tma(False)
-    if args.no_umma:
-        eng.set_umma(False)
+    if args.umma:
+        eng.set_umma(True)
+    if args.row_filter >= 0:
+        eng.set_row_filter(args.row_filter)
     pn, pc = E.make_params(NO_CELLS), None
     mode, flags = E.MODE_LOGSPACE, 0
     if args.workload == "c3":
@@ -373,7 +376,8 @@ def run_b200(args):
                 "every stage against its own algorithmic bytes; the stages are issue-slot bound (CUDA cores) or, for the "
                 "row filter, split between CUDA-core preparation and tcgen05 MMAs",
         "dominant_stage": dom,
-        "row_filter_path": "cuda-core" if args.no_umma else "tcgen05 (kind::f16 hi/lo, TMEM accumulators)",
+        "row_filter_path": ("tcgen05 (kind::f16 hi/lo, TMEM accumulators)" if args.umma else
+                            "fma (register-tiled FIR)" if args.row_filter == 0 else "mma.sync m16n8k16 fp16 hi/lo"),
         "kernels": kernels,
         "stage_ms_per_step": stage_ms,
     }

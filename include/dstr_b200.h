@@ -186,6 +186,10 @@ int dstr_set_tma(dstr_ctx* ctx, int enabled);
  * it): the CUDA-core kernel, which measures 6-10 % faster on B200.  Both paths
  * pass the same parity tests. */
 int dstr_set_umma(dstr_ctx* ctx, int enabled);
+/* CUDA-core row filter variant: 1 (default; environment DSTR_ROW_FILTER) = the even / odd FIRs and the rank-J
+ * correction as mma.sync m16n8k16 products on fp16 hi/lo operand pairs (csrc/dstr_rows_mma.cuh), 0 = the
+ * register-tiled FMA kernel of round 1.  Same operator tables, same parity tests. */
+int dstr_set_row_filter(dstr_ctx* ctx, int kind);
 /* geometry of the tensor-core row filter for a band of width n:
  * info = {eligible, passes, outputs per pass, k chunks, table bytes, shared memory bytes, outputs, padded K}
  * (tables are sized for notch width s; s <= 0 reports the geometry only) */
