@@ -991,7 +991,9 @@ int launch_filter_umma(const Pass& P, int l, cudaStream_t st) {
         ctx->d_um_scratch[l] = nullptr;
         ctx->um_scratch_bytes[l] = 0;
         CK(ctx, cudaMalloc(&ctx->d_um_scratch[l], need));
-        CK(ctx, cudaMemset(ctx->d_um_scratch[l], 0, need));  // rows / chunks never written must stay finite
+        // rows / chunks never written must stay finite.  Ordered on the launching stream: the engine's streams are
+        // non-blocking, so a memset on the legacy default stream could still be running when the kernel starts
+        CK(ctx, cudaMemsetAsync(ctx->d_um_scratch[l], 0, need, st));
         ctx->um_scratch_bytes[l] = need;
     }
     ua.scratch = ctx->d_um_scratch[l];
@@ -2167,8 +2169,12 @@ int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_
     const int Z = ctx->last_z;
     const LevelGeom& g = ctx->geom[level];
     if (what == DSTR_FETCH_CA || what == DSTR_FETCH_CH) {
+        // the workspace holds the LAST sub-chunk only (last_z planes): a buffer of any other size means the caller
+        // expects planes that are not there
         const size_t need = sizeof(float) * (size_t)Z * g.H * g.W;
-        if (host_bytes < need) return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: buffer too small");
+        if (host_bytes != need)
+            return fail(ctx, DSTR_E_ARG, "dstr_debug_fetch: buffer does not match the planes of the last sub-chunk "
+                                         "(dstr_set_subchunk >= Z keeps a whole chunk resident)");
         const float* src = (what == DSTR_FETCH_CA) ? ctx->d_A[level] : ctx->d_H[level];
         for (int z = 0; z < Z; ++z) {
             CK(ctx, cudaMemcpy2D((float*)host_buf + (size_t)z * g.H * g.W, sizeof(float) * g.W,

@@ -390,8 +390,7 @@ notch_umma_kernel(UmmaLevelArgs a, const PlaneStat* __restrict__ pstat, Dispatch
                                 // descriptors differ from the constant bases only in the 14-bit start-address field
                                 const uint64_t dEH = dA0 + aS + (uint64_t)(j * 256);
                                 const uint64_t dTRh = dTRh0 + roff16 + (uint64_t)(j * 16);
-                                um_mma(tE, dEH, dTRh, idesc, e_on);
-                                e_on = 1;
+                                um_mma(tE, dEH, dTRh, idesc, (e_on | (uint32_t)j) ? 1u : 0u);
                                 if (uc.r3) {
                                     um_mma(tE, dEH + (UM_CHUNK_BYTES / 16), dTRh, idesc, 1u);
                                     um_mma(tE, dEH, dTRh + (uint64_t)(uc.tr_bytes >> 4), idesc, 1u);
@@ -406,8 +405,7 @@ notch_umma_kernel(UmmaLevelArgs a, const PlaneStat* __restrict__ pstat, Dispatch
                                         um_mma(tE, dEL, dTBh, idesc, 1u);
                                         um_mma(tE, dEH, dTBl, idesc, 1u);
                                     }
-                                    um_mma(tO, dOH, dTBh, idesc, o_on);
-                                    o_on = 1;
+                                    um_mma(tO, dOH, dTBh, idesc, (o_on | (uint32_t)j) ? 1u : 0u);
                                     um_mma(tO, dOL, dTBh, idesc, 1u);
                                     um_mma(tO, dOH, dTBl, idesc, 1u);
                                 }
@@ -417,6 +415,9 @@ notch_umma_kernel(UmmaLevelArgs a, const PlaneStat* __restrict__ pstat, Dispatch
                             if (p == a.P - 1 && c == a.NC - 1) um_arrive(&s_scratch_free[buf]);
                         }
                         __syncwarp();
+                        // accumulate flags are kept by every lane (whichever lane is elected next sees them)
+                        e_on = 1;
+                        if (bd.in(c)) o_on = 1;
                         roff16 += 32u;  // 32 k = 4 blocks of 128 bytes
                         if (++s == UM_STAGES) {
                             s = 0;
@@ -600,11 +601,13 @@ notch_umma_kernel(UmmaLevelArgs a, const PlaneStat* __restrict__ pstat, Dispatch
                                 }
                                 unique = (hi_cnt - lo_cnt) == 1;
                             }
-                            // res is the key itself or a lower bound of the single key left in the bracket
+                            // res is the key itself or a lower bound of the single key left in the bracket; on the
+                            // positive side the bracket starts above the zeros (lo_cnt = cle0), the prefix may not
+                            const unsigned lower = negside ? res : max(res, KZ + 1u);
                             kk1 = 0xffffffffu;
 #pragma unroll
                             for (int i = 0; i < EPL; ++i)
-                                if (key[i] >= res) kk1 = min(kk1, key[i]);
+                                if (key[i] >= lower) kk1 = min(kk1, key[i]);
                             kk1 = __reduce_min_sync(0xffffffffu, kk1);
                         }
                         med = key2f(kk1);

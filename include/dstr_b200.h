@@ -173,6 +173,9 @@ int dstr_set_profiling(dstr_ctx* ctx, int enabled);
 int dstr_get_timers(dstr_ctx* ctx, double* ms_out /*[DSTR_NUM_TIMERS]*/, uint64_t* launches_out);
 int dstr_reset_timers(dstr_ctx* ctx);
 int dstr_set_debug_stop(dstr_ctx* ctx, int stage);
+/* Copies an intermediate of the LAST sub-chunk processed (host chunks are cut into dstr_set_subchunk planes, default
+ * 4; device chunks into max_planes).  Z of the layouts above is that sub-chunk's plane count and host_bytes of a
+ * coefficient fetch must match it exactly (DSTR_E_ARG otherwise). */
 int dstr_debug_fetch(dstr_ctx* ctx, int what, int level, void* host_buf, uint64_t host_bytes);
 /* 1 (default): the per-level histogram / Otsu / row-filter branches run on side streams next to
  * the analysis and synthesis chains; 0: every kernel on the compute stream in stage order */
