@@ -373,8 +373,9 @@ def run_b200(args):
         "traffic": measured.get("dram_bytes_per_step"), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes,
         "note": "headline = 4 B/px (u16 in + u16 out) x pixels of the chunk / device time of the whole step; kernels[] lists "
-                "every stage against its own algorithmic bytes; the stages are issue-slot bound (CUDA cores) or, for the "
-                "row filter, split between CUDA-core preparation and tcgen05 MMAs",
+                "every stage against its own algorithmic bytes and the DRAM bytes ncu measured for it (profiles/traffic.json); "
+                "analysis and final synthesis run at 0.6 of the HBM peak, the row filter is issue-slot bound (median "
+                "selection, operand construction) with its contractions on the tensor pipe",
         "dominant_stage": dom,
         "row_filter_path": ("tcgen05 (kind::f16 hi/lo, TMEM accumulators)" if args.umma else
                             "fma (register-tiled FIR)" if args.row_filter == 0 else "mma.sync m16n8k16 fp16 hi/lo"),
