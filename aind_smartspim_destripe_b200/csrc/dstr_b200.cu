@@ -5,6 +5,7 @@
 #include "dstr_kernels.cuh"
 #include "dstr_notch_umma.cuh"
 #include "dstr_rows_mma.cuh"
+#include "dstr_dual_band.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -115,6 +116,13 @@ struct dstr_ctx {
     // per-CTA operand scratch of the tcgen05 row filter, one per level (the levels' filters run
     // concurrently on the side streams)
     uint8_t* d_um_scratch[kMaxLevels + 1] = {};
+    // dual-band mode (dstr_dual_band_chunk): [0] background band filtered, [1] foreground band filtered, [2] clamped
+    // band (float32, zcap planes each), per-plane thresholds, 1 / flat, staging for host chunks
+    float* d_db[3] = {nullptr, nullptr, nullptr};
+    float* d_db_thr = nullptr;
+    float* d_db_invflat = nullptr;
+    void* d_db_in = nullptr;
+    uint16_t* d_db_out = nullptr;
     size_t um_scratch_bytes[kMaxLevels + 1] = {};
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     unsigned long long host_it = 0;  // sub-chunks streamed so far (staging buffer = host_it & 1), across calls
@@ -832,6 +840,8 @@ int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem, 
 }
 
 // Everything one chunk pass needs to launch its kernels.
+constexpr int kModeForceCells = 2;  // internal: every plane uses the `cells` tables (second band of the dual-band mode)
+
 struct Pass {
     dstr_ctx* ctx;
     const void* d_in;
@@ -1238,7 +1248,8 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
     P.dp.max_thr_cells = cells.max_threshold;
     P.dp.max_thr_nocells = no_cells.max_threshold;
     P.dp.high_int = high_int;
-    P.dp.mode = (mode == DSTR_MODE_DISPATCH) ? 1 : 0;
+    P.dp.mode = (mode == DSTR_MODE_DISPATCH) ? 1 : (mode == kModeForceCells ? 2 : 0);
+    P.dp.notch_only = (flags & DSTR_FLAG_NOTCH_ONLY) ? 1 : 0;
     ctx->last_levels = L;
     ctx->last_z = z;
     ctx->last_dp = P.dp;
@@ -1257,7 +1268,8 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
         if (L > 0) {
             {
                 ScopedTimer t(ctx, 2);
-                for (int l = 1; l <= L; ++l) RC(launch_hist(P, l, st));
+                if (!P.dp.notch_only)
+                    for (int l = 1; l <= L; ++l) RC(launch_hist(P, l, st));
             }
             {
                 ScopedTimer t(ctx, 3);
@@ -1290,7 +1302,7 @@ int process_device(dstr_ctx* ctx, const void* d_in, int in_dtype, void* d_out, i
         CK(ctx, cudaEventRecord(ctx->ev_an[l], st));
         cudaStream_t side = ctx->s_side[(l - 1) % kSideStreams];
         CK(ctx, cudaStreamWaitEvent(side, ctx->ev_an[l], 0));
-        RC(launch_hist(P, l, side));
+        if (!P.dp.notch_only) RC(launch_hist(P, l, side));
         RC(launch_otsu(P, l, 1, side));
         RC(launch_filter_level(P, l, side));
         CK(ctx, cudaEventRecord(ctx->ev_flt[l], side));
@@ -1523,6 +1535,12 @@ int dstr_destroy(dstr_ctx* ctx) {
             if (ctx->d_pyr[l][b2]) cudaFree(ctx->d_pyr[l][b2]);
     for (int l = 0; l <= kMaxLevels; ++l)
         if (ctx->d_um_scratch[l]) cudaFree(ctx->d_um_scratch[l]);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->d_db[i]) cudaFree(ctx->d_db[i]);
+    if (ctx->d_db_thr) cudaFree(ctx->d_db_thr);
+    if (ctx->d_db_invflat) cudaFree(ctx->d_db_invflat);
+    if (ctx->d_db_in) cudaFree(ctx->d_db_in);
+    if (ctx->d_db_out) cudaFree(ctx->d_db_out);
     if (ctx->d_lstat) cudaFree(ctx->d_lstat);
     if (ctx->d_pstat) cudaFree(ctx->d_pstat);
     if (ctx->d_flat) cudaFree(ctx->d_flat);  // d_dark lives in the same allocation
@@ -2136,6 +2154,151 @@ int dstr_downscale2x(dstr_ctx* ctx, const uint16_t* in, int Z, int H, int W, uin
     if (!rc && es != cudaSuccess) rc = fail(ctx, (int)es, cudaGetErrorString(es));
     if (!in_dev && d_in) cudaFree(d_in);
     if (!out_dev && d_out) cudaFree(d_out);
+    return rc;
+}
+
+// Classic dual-band mode (dstr_dual_band.cuh).  in / out: host or device pointers, thresholds and flat: host pointers.
+int dstr_dual_band_chunk(dstr_ctx* ctx, const void* in, int in_dtype, uint16_t* out, int Z, float sigma_fg,
+                         float sigma_bg, int level, const float* thresholds, float crossover, float dark,
+                         const float* flat) {
+    if (!ctx) return DSTR_E_ARG;
+    if (!in || !out || Z <= 0 || !thresholds) return fail(ctx, DSTR_E_ARG, "dstr_dual_band_chunk: bad argument");
+    if (in_dtype != DSTR_U16 && in_dtype != DSTR_F32) return fail(ctx, DSTR_E_ARG, "dstr_dual_band_chunk: bad dtype");
+    if (sigma_fg < 0.f || sigma_bg < 0.f || !(crossover > 0.f)) return fail(ctx, DSTR_E_ARG, "dstr_dual_band_chunk: bad sigma / crossover");
+    const int L = level < 0 ? ctx->Lmax : level;
+    if (L > ctx->Lalloc) return fail(ctx, DSTR_E_UNSUPPORTED, "level exceeds pywt.dwtn_max_level for this plane shape by more than 4");
+    CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
+    cudaStream_t st = ctx->s_comp;
+    const size_t plane_px = (size_t)ctx->H * ctx->W;
+    const int zcap = ctx->zcap;
+    const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
+    const size_t in_pb = plane_px * dtype_size(in_dtype);
+    const bool any = sigma_fg > 0.f || sigma_bg > 0.f;
+    const bool single = sigma_fg > 0.f && sigma_fg == sigma_bg;
+    for (int i = 0; i < 3; ++i)
+        if (!ctx->d_db[i]) CK(ctx, cudaMalloc(&ctx->d_db[i], sizeof(float) * plane_px * zcap));
+    if (!ctx->d_db_thr) CK(ctx, cudaMalloc(&ctx->d_db_thr, sizeof(float) * zcap));
+    if (!in_dev && !ctx->d_db_in) CK(ctx, cudaMalloc(&ctx->d_db_in, 4 * plane_px * zcap));
+    if (!out_dev && !ctx->d_db_out) CK(ctx, cudaMalloc(&ctx->d_db_out, 2 * plane_px * zcap));
+    const float* d_invflat = nullptr;
+    if (flat) {
+        if (!ctx->d_db_invflat) CK(ctx, cudaMalloc(&ctx->d_db_invflat, sizeof(float) * plane_px));
+        std::vector<float> inv(plane_px);
+        for (size_t i = 0; i < plane_px; ++i) inv[i] = 1.0f / flat[i];
+        CK(ctx, cudaMemcpyAsync(ctx->d_db_invflat, inv.data(), sizeof(float) * plane_px, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaStreamSynchronize(st));
+        d_invflat = ctx->d_db_invflat;
+    }
+    // pystripe: s_l = H_l sigma / H (rows of the image); the tables here use min(H, W) (filtering.py:180)
+    const float fix = (float)((double)std::min(ctx->H, ctx->W) / (double)ctx->H);
+    dstr_params pb = {(sigma_bg > 0.f ? sigma_bg : sigma_fg) * fix, 0.f, L};
+    dstr_params pf = {(sigma_fg > 0.f ? sigma_fg : sigma_bg) * fix, 0.f, L};
+    if (any)
+        for (int l = 1; l <= L; ++l) {
+            int rc = build_taps(ctx, l, pf.sigma, pb.sigma);  // cells tables = foreground band, no_cells = background
+            if (rc) return rc;
+        }
+    const int blocks = (int)std::min<size_t>((plane_px + 255) / 256, (size_t)ctx->sm_count * 8);
+    const int band_flags = DSTR_FLAG_NOTCH_ONLY | DSTR_FLAG_EXPM1 | DSTR_FLAG_NO_SYNC;
+    for (int z0 = 0; z0 < Z; z0 += zcap) {
+        const int zn = std::min(zcap, Z - z0);
+        const void* src = (const char*)in + (size_t)z0 * in_pb;
+        if (!in_dev) {
+            CK(ctx, cudaMemcpyAsync(ctx->d_db_in, src, in_pb * zn, cudaMemcpyHostToDevice, st));
+            src = ctx->d_db_in;
+        }
+        CK(ctx, cudaMemcpyAsync(ctx->d_db_thr, thresholds + z0, sizeof(float) * zn, cudaMemcpyHostToDevice, st));
+        dim3 grid(blocks, zn);
+        BlendArgs ba;
+        ba.bgf = nullptr;
+        ba.fgf = nullptr;
+        ba.thr = ctx->d_db_thr;
+        ba.inv_flat = d_invflat;
+        ba.crossover = crossover;
+        ba.dark = dark;
+        ba.single = single ? 1 : 0;
+        int rc = 0;
+        if (single) {
+            rc = process_device(ctx, src, in_dtype, ctx->d_db[1], DSTR_F32, zn, pf, pb, 0.f, kModeForceCells, band_flags, L);
+            if (rc) return rc;
+            ba.fgf = ctx->d_db[1];
+        } else {
+            if (sigma_bg > 0.f) {
+                if (in_dtype == DSTR_U16) clamp_band_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, ctx->d_db[2], plane_px, ctx->d_db_thr, 0);
+                else clamp_band_kernel<float><<<grid, 256, 0, st>>>((const float*)src, ctx->d_db[2], plane_px, ctx->d_db_thr, 0);
+                ctx->launches++;
+                rc = process_device(ctx, ctx->d_db[2], DSTR_F32, ctx->d_db[0], DSTR_F32, zn, pf, pb, 0.f, DSTR_MODE_LOGSPACE, band_flags, L);
+                if (rc) return rc;
+                ba.bgf = ctx->d_db[0];
+            }
+            if (sigma_fg > 0.f) {
+                if (in_dtype == DSTR_U16) clamp_band_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, ctx->d_db[2], plane_px, ctx->d_db_thr, 1);
+                else clamp_band_kernel<float><<<grid, 256, 0, st>>>((const float*)src, ctx->d_db[2], plane_px, ctx->d_db_thr, 1);
+                ctx->launches++;
+                rc = process_device(ctx, ctx->d_db[2], DSTR_F32, ctx->d_db[1], DSTR_F32, zn, pf, pb, 0.f, kModeForceCells, band_flags, L);
+                if (rc) return rc;
+                ba.fgf = ctx->d_db[1];
+            }
+        }
+        uint16_t* dst = out_dev ? out + (size_t)z0 * plane_px : ctx->d_db_out;
+        if (in_dtype == DSTR_U16) dual_band_blend_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, dst, plane_px, ba);
+        else dual_band_blend_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, plane_px, ba);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+        if (!out_dev)
+            CK(ctx, cudaMemcpyAsync(out + (size_t)z0 * plane_px, dst, 2 * plane_px * zn, cudaMemcpyDeviceToHost, st));
+        // the next batch reuses the staging buffers and thresholds
+        CK(ctx, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int dstr_histogram_u16(dstr_ctx* ctx, const uint16_t* in, int Z, uint32_t* hist) {
+    if (!ctx) return DSTR_E_ARG;
+    if (!in || !hist || Z <= 0) return fail(ctx, DSTR_E_ARG, "dstr_histogram_u16: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rcd = drain_async(ctx);
+        if (rcd) return rcd;
+    }
+    static std::mutex mtx;
+    static bool done[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        if (!done[ctx->device & 63]) {
+            CK(ctx, cudaFuncSetAttribute(hist_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+            done[ctx->device & 63] = true;
+        }
+    }
+    cudaStream_t st = ctx->s_comp;
+    const size_t plane_px = (size_t)ctx->H * ctx->W;
+    const bool in_dev = is_device_ptr(in);
+    uint16_t* d_in = nullptr;
+    unsigned* d_hist = nullptr;
+    int rc = 0;
+    auto ck = [&](cudaError_t e) {
+        if (e != cudaSuccess && !rc) rc = fail(ctx, (int)e, cudaGetErrorString(e));
+    };
+    ck(cudaMalloc(&d_hist, sizeof(unsigned) * 65536 * (size_t)Z));
+    if (!rc && !in_dev) {
+        ck(cudaMalloc(&d_in, 2 * plane_px * Z));
+        if (!rc) ck(cudaMemcpyAsync(d_in, in, 2 * plane_px * Z, cudaMemcpyHostToDevice, st));
+    }
+    if (!rc) {
+        ck(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * 65536 * (size_t)Z, st));
+        dim3 grid((unsigned)((plane_px + HU_PX_PER_BLOCK - 1) / HU_PX_PER_BLOCK), Z);
+        hist_u16_kernel<<<grid, HU_THREADS, 131072, st>>>(in_dev ? in : d_in, plane_px, d_hist);
+        ctx->launches++;
+        ck(cudaGetLastError());
+        ck(cudaMemcpyAsync(hist, d_hist, sizeof(unsigned) * 65536 * (size_t)Z, cudaMemcpyDeviceToHost, st));
+    }
+    ck(cudaStreamSynchronize(st));
+    if (d_in) cudaFree(d_in);
+    if (d_hist) cudaFree(d_hist);
     return rc;
 }
 

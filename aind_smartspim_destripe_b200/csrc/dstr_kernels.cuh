@@ -75,7 +75,8 @@ struct DispatchParams {
     float max_thr_cells;
     float max_thr_nocells;
     float high_int;
-    int mode;  // 0: always no_cells; 1: per-plane dispatch
+    int mode;  // 0: always no_cells; 1: per-plane dispatch; 2: always cells (second pass of the dual-band mode)
+    int notch_only;  // 1: no Otsu mask / median in-painting, every coefficient goes through the notch (dual-band mode)
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -88,6 +89,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 __device__ __forceinline__ int plane_uses_cells(const PlaneStat& ps, const DispatchParams& dp) {
     // filtering.py:462  fore_mean > back_mean and fore_mean > microscope_high_int
     if (dp.mode == 0) return 0;
+    if (dp.mode == 2) return 1;
     const double fg = ps.fg_cnt ? ps.fg_sum / (double)ps.fg_cnt : 0.0;
     const double bg = ps.bg_cnt ? ps.bg_sum / (double)ps.bg_cnt : 0.0;
     return (fg > bg && fg > (double)dp.high_int) ? 1 : 0;
@@ -823,6 +825,16 @@ otsu_kernel(LevelStat* __restrict__ lstat_base, size_t level_stride, int stat_st
     const float first = __uint_as_float(~st->qmin_inv);
     const float last = __uint_as_float(st->qmax_bits);
     const float max_thr = plane_uses_cells(pstat[z], dp) ? dp.max_thr_cells : dp.max_thr_nocells;
+    if (dp.notch_only) {
+        // nothing is masked: thr only scales the row-filter operands (max |cH|), the mask test never fires
+        if (lane == 0) {
+            st->otsu_raw = last;
+            st->otsu_bin = -1;
+            st->thr = __fsqrt_rn(last);
+            st->thr_q = __int_as_float(0x7f800000);
+        }
+        return;
+    }
 
     float otsu;
     int best_i = -1;

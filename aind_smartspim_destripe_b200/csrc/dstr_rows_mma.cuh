@@ -95,12 +95,14 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     const float thr_q = st->thr_q;
     // power-of-two pre-scale: |x| <= thr, so the scaled operands stay below 2^15 (fp16 range)
     float scale = 1.0f;
+    bool coarse_ok = false;  // |x| scale < 2^15 for every unmasked x: the fp16 images are finite
     {
         const float thr = st->thr;
         if (thr > 0.f && thr < 1e30f) {
             int e;
             frexpf(thr, &e);
             scale = ldexpf(1.0f, max(-24, min(14 - e, 40)));
+            coarse_ok = sqrtf(thr_q) * scale < 32000.0f;
         }
     }
     const int nh = a.nh;
@@ -129,16 +131,28 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
 #pragma unroll
             for (int i = 0; i < EPL; ++i) key[i] = __float_as_uint(gl[32 * i]);
         }
+        // fp16 images of the scaled zero-filled row, two per register (+inf past the end): the median search below
+        // does its first, coarse bisection on these with packed compares (any rounding is monotone, so the order
+        // statistics of the images bracket those of the floats)
+        constexpr int HP = (EPL + 1) / 2;
+        __half2 hx[HP];
+        float hprev = 0.f;
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
             const int e = lane + 32 * i;
             const float c = __uint_as_float(key[i]);
             key[i] = 0xffffffffu;
             bool m = false;
+            float hv = __int_as_float(0x7f800000);
             if (e < n) {
                 m = __fmul_rn(c, c) > thr_q;
-                key[i] = f2key(m ? 0.0f : (c + 0.0f));
+                const float x = m ? 0.0f : (c + 0.0f);
+                key[i] = f2key(x);  // zero-filled background, canonical +0
+                hv = x * scale;
             }
+            if (i & 1) hx[i >> 1] = __floats2half2_rn(hprev, hv);
+            else if (i == EPL - 1) hx[i >> 1] = __floats2half2_rn(hv, __int_as_float(0x7f800000));
+            hprev = hv;
             const unsigned mbits = __ballot_sync(0xffffffffu, m);
             if (lane == 0) s_mask[wid * EPL + i] = mbits;
         }
@@ -146,48 +160,114 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
         const unsigned KZ = 0x80000000u;
         const int k1 = (n - 1) >> 1, k2 = n >> 1;
         int cneg = 0, cle0 = 0;
+        const bool nomask = thr_q == __int_as_float(0x7f800000);  // notch-only pass: the in-painting value is never used
+        if (!nomask) {
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            cneg += (key[i] < KZ) ? 1 : 0;
-            cle0 += (key[i] <= KZ) ? 1 : 0;
+            for (int i = 0; i < EPL; ++i) {
+                cneg += (key[i] < KZ) ? 1 : 0;
+                cle0 += (key[i] <= KZ) ? 1 : 0;
+            }
+            cneg = __reduce_add_sync(0xffffffffu, cneg);
+            cle0 = __reduce_add_sync(0xffffffffu, cle0);
         }
-        cneg = __reduce_add_sync(0xffffffffu, cneg);
-        cle0 = __reduce_add_sync(0xffffffffu, cle0);
         float med;
-        if (cneg <= k1 && k2 < cle0) {
+        if (nomask || (cneg <= k1 && k2 < cle0)) {
             med = 0.f;
         } else {
-            unsigned res;
-            int lo_cnt, hi_cnt;
-            if (k1 < cneg) {
-                res = 0u;
-                lo_cnt = 0;
-                hi_cnt = cneg;
-            } else {
-                res = KZ;
-                lo_cnt = cneg;
-                hi_cnt = n;
-            }
-            bool unique = (hi_cnt - lo_cnt) == 1;
-            for (int b = 30; b >= 0 && !unique; --b) {
-                const unsigned trial = res | (1u << b);
-                int cnt = 0;
+            unsigned kk1 = 0xffffffffu;  // key of the order statistic k1
+            if (coarse_ok) {
+                // stage 1: bisection over the 16-bit ordered keys of the fp16 images; invariant
+                //   #{h < t(res16)} = lo_cnt <= k1 < hi_cnt = #{h < t(hi16)};  ends when one element is bracketed
+                unsigned res16 = 0u, hi16 = 0xfc00u;  // t(0xfc00) = +inf
+                int lo_cnt = 0, hi_cnt = n;
+                for (int b = 15; b >= 0 && (hi_cnt - lo_cnt) != 1; --b) {
+                    const unsigned trial = res16 | (1u << b);
+                    const __half2 t2 = __half2half2(__ushort_as_half((unsigned short)((trial & 0x8000u) ? (trial & 0x7fffu) : (~trial & 0xffffu))));
+                    __half2 a0 = __half2half2(__ushort_as_half((unsigned short)0)), a1 = a0;
 #pragma unroll
-                for (int i = 0; i < EPL; ++i) cnt += (key[i] < trial) ? 1 : 0;
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                if (cnt <= k1) {
-                    res = trial;
-                    lo_cnt = cnt;
-                } else {
-                    hi_cnt = cnt;
+                    for (int i = 0; i < HP; ++i) {
+                        if (i & 1) a1 = __hadd2(a1, __hlt2(hx[i], t2));
+                        else a0 = __hadd2(a0, __hlt2(hx[i], t2));
+                    }
+                    a0 = __hadd2(a0, a1);  // at most EPL per half: exact in fp16
+                    int cnt = __float2int_rn(__low2float(a0) + __high2float(a0));
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                    if (cnt <= k1) {
+                        res16 = trial;
+                        lo_cnt = cnt;
+                    } else {
+                        hi16 = trial;
+                        hi_cnt = cnt;
+                    }
                 }
-                unique = (hi_cnt - lo_cnt) == 1;
-            }
-            unsigned kk1 = 0xffffffffu;
+                // stage 2: the bracketed elements are contiguous in float order; rank r among them
+                const __half2 lo2 = __half2half2(__ushort_as_half((unsigned short)((res16 & 0x8000u) ? (res16 & 0x7fffu) : (~res16 & 0xffffu))));
+                const __half2 hi2 = __half2half2(__ushort_as_half((unsigned short)((hi16 & 0x8000u) ? (hi16 & 0x7fffu) : (~hi16 & 0xffffu))));
+                unsigned cmin = 0xffffffffu, cmax = 0u;
 #pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if (key[i] >= res) kk1 = min(kk1, key[i]);
-            kk1 = __reduce_min_sync(0xffffffffu, kk1);
+                for (int i = 0; i < HP; ++i) {
+                    const unsigned mk = __hge2_mask(hx[i], lo2) & __hlt2_mask(hx[i], hi2);
+                    if (mk & 0xffffu) {
+                        cmin = min(cmin, key[2 * i]);
+                        cmax = max(cmax, key[2 * i]);
+                    }
+                    if (2 * i + 1 < EPL && (mk >> 16)) {
+                        cmin = min(cmin, key[2 * i + 1]);
+                        cmax = max(cmax, key[2 * i + 1]);
+                    }
+                }
+                cmin = __reduce_min_sync(0xffffffffu, cmin);
+                cmax = __reduce_max_sync(0xffffffffu, cmax);
+                const int mc_ = hi_cnt - lo_cnt, r = k1 - lo_cnt;
+                if (r == 0) {
+                    kk1 = cmin;
+                } else if (r == mc_ - 1) {
+                    kk1 = cmax;
+                } else {  // several distinct floats inside one fp16 step: smallest key v with #{key <= v} > k1
+                    unsigned lo = cmin, hi = cmax;
+                    while (lo < hi) {
+                        const unsigned mid = lo + ((hi - lo) >> 1);
+                        int cnt = 0;
+#pragma unroll
+                        for (int i = 0; i < EPL; ++i) cnt += (key[i] <= mid) ? 1 : 0;
+                        cnt = __reduce_add_sync(0xffffffffu, cnt);
+                        if (cnt > k1) hi = mid;
+                        else lo = mid + 1u;
+                    }
+                    kk1 = lo;
+                }
+            } else {
+                unsigned res;
+                int lo_cnt, hi_cnt;
+                if (k1 < cneg) {
+                    res = 0u;
+                    lo_cnt = 0;
+                    hi_cnt = cneg;
+                } else {
+                    res = KZ;
+                    lo_cnt = cneg;
+                    hi_cnt = n;
+                }
+                bool unique = (hi_cnt - lo_cnt) == 1;
+                for (int b = 30; b >= 0 && !unique; --b) {
+                    const unsigned trial = res | (1u << b);
+                    int cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) cnt += (key[i] < trial) ? 1 : 0;
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                    if (cnt <= k1) {
+                        res = trial;
+                        lo_cnt = cnt;
+                    } else {
+                        hi_cnt = cnt;
+                    }
+                    unique = (hi_cnt - lo_cnt) == 1;
+                }
+#pragma unroll
+                for (int i = 0; i < EPL; ++i)
+                    if (key[i] >= res) kk1 = min(kk1, key[i]);
+                kk1 = __reduce_min_sync(0xffffffffu, kk1);
+            }
             med = key2f(kk1);
             if (k2 != k1) {
                 int cle = 0;

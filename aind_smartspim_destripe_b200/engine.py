@@ -110,6 +110,11 @@ def load_library() -> C.CDLL:
             "dstr_set_umma": (C.c_int, [vp, C.c_int]),
             "dstr_set_row_filter": (C.c_int, [vp, C.c_int]),
             "dstr_notch_umma_info": (C.c_int, [C.c_int, C.c_double, ip]),
+            "dstr_dual_band_chunk": (
+                C.c_int,
+                [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, vp],
+            ),
+            "dstr_histogram_u16": (C.c_int, [vp, vp, C.c_int, vp]),
             "dstr_notch_umma_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp, ip]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
             "dstr_blosc_available": (C.c_int, [C.c_int]),
@@ -133,7 +138,7 @@ EXPORTED_SYMBOLS = (
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
     "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_set_umma dstr_set_row_filter dstr_notch_umma_info "
     "dstr_notch_umma_apply_host dstr_downscale2x dstr_set_pyramid_outputs dstr_blosc_available dstr_blosc_compress "
-    "dstr_blosc_decompress"
+    "dstr_blosc_decompress dstr_dual_band_chunk dstr_histogram_u16"
 ).split()
 
 
@@ -402,6 +407,59 @@ class DestripeEngine:
             flags,
         )
         return out
+
+    def dual_band_chunk(self, data: np.ndarray, sigma_fg: float, sigma_bg: float, thresholds, level: int = -1,
+                        crossover: float = 10.0, dark: float = 0.0, flat: Optional[np.ndarray] = None,
+                        out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Classic dual-band filter of a (Z, H, W) host chunk (``dstr_dual_band_chunk``) -> uint16."""
+        if data.ndim != 3 or data.shape[1:] != (self.H, self.W):
+            raise ValueError(f"expected (Z, {self.H}, {self.W}) planes, got {data.shape}")
+        data = np.ascontiguousarray(data)
+        Z = data.shape[0]
+        thr = np.ascontiguousarray(np.broadcast_to(np.asarray(thresholds, dtype=np.float32), (Z,)))
+        if out is None:
+            out = np.empty(data.shape, dtype=np.uint16)
+        if out.dtype != np.uint16 or not out.flags.c_contiguous or out.shape != data.shape:
+            raise ValueError("out must be a C-contiguous uint16 array with the input's shape")
+        fptr = None
+        if flat is not None:
+            flat = np.ascontiguousarray(flat, dtype=np.float32)
+            if flat.shape != (self.H, self.W):
+                raise ValueError(f"flat must have shape ({self.H}, {self.W})")
+            fptr = flat.ctypes.data_as(C.c_void_p)
+        rc = self.lib.dstr_dual_band_chunk(
+            self.ctx, data.ctypes.data_as(C.c_void_p), _np_dtype_code(data.dtype), out.ctypes.data_as(C.c_void_p), Z,
+            float(sigma_fg), float(sigma_bg), int(level), thr.ctypes.data_as(C.POINTER(C.c_float)), float(crossover),
+            float(dark), fptr,
+        )
+        self._ck(rc, "dstr_dual_band_chunk")
+        return out
+
+    def dual_band_chunk_ptr(self, in_ptr, in_code, out_ptr, Z, sigma_fg, sigma_bg, thresholds, level=-1, crossover=10.0,
+                            dark=0.0, flat: Optional[np.ndarray] = None):
+        """``dstr_dual_band_chunk`` on raw (host or device) pointers; ``thresholds``: (Z,) float32 host array."""
+        thr = np.ascontiguousarray(thresholds, dtype=np.float32)
+        if thr.shape != (int(Z),):
+            raise ValueError("one threshold per plane")
+        fptr = None
+        if flat is not None:
+            flat = np.ascontiguousarray(flat, dtype=np.float32)
+            fptr = flat.ctypes.data_as(C.c_void_p)
+        rc = self.lib.dstr_dual_band_chunk(self.ctx, in_ptr, in_code, out_ptr, int(Z), float(sigma_fg), float(sigma_bg),
+                                           int(level), thr.ctypes.data_as(C.POINTER(C.c_float)), float(crossover),
+                                           float(dark), fptr)
+        self._ck(rc, "dstr_dual_band_chunk")
+
+    def histogram_u16(self, data: np.ndarray) -> np.ndarray:
+        """Exact per-plane histogram of a (Z, H, W) uint16 chunk -> (Z, 65536) uint32."""
+        if data.ndim != 3 or data.shape[1:] != (self.H, self.W) or data.dtype != np.uint16:
+            raise ValueError(f"expected (Z, {self.H}, {self.W}) uint16 planes")
+        data = np.ascontiguousarray(data)
+        hist = np.empty((data.shape[0], 65536), dtype=np.uint32)
+        rc = self.lib.dstr_histogram_u16(self.ctx, data.ctypes.data_as(C.c_void_p), data.shape[0],
+                                         hist.ctypes.data_as(C.c_void_p))
+        self._ck(rc, "dstr_histogram_u16")
+        return hist
 
     def plane_stats(self, data: np.ndarray, high_int: float = 2700.0, threshold_mask: float = 0.3):
         if data.ndim != 3 or data.shape[1:] != (self.H, self.W):

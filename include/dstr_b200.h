@@ -47,6 +47,9 @@ typedef struct dstr_ctx dstr_ctx;
                                    host buffers: both stay owned by the call until dstr_synchronize; the
                                    next chunk's H2D then overlaps this chunk's D2H) */
 
+#define DSTR_FLAG_NOTCH_ONLY 16 /* no Otsu mask and no median in-painting: every cH coefficient goes through the
+                                   notch (the sub-band filter of the dual-band mode) */
+
 /* Filter parameters = the reference's config dict {wavelet:"db3", level, sigma, max_threshold}
  * (run_capsule.py:377-388).  level < 0 means "None" (maximum level). */
 typedef struct dstr_params {
@@ -183,6 +186,22 @@ int dstr_set_overlap(dstr_ctx* ctx, int enabled);
 /* 1 (default): level-1 analysis through the TMA-staged kernel (cp.async.bulk ring + mbarrier) when
  * W >= 256 and rows are 16-byte multiples; 0: always the register-streaming kernel */
 int dstr_set_tma(dstr_ctx* ctx, int enabled);
+
+/* Classic dual-band mode (pystripe `filter_streaks`; the picture under "Dual-band" in the reference README; not in
+ * the reference sources, see SURVEY.md Appendix B — parity is against oracle/dual_band.py only):
+ *   bg = min(img, T), fg = max(img, T); each band through log1p -> wavedec2(db3, level) -> packed-rfft notch on
+ *   every cH_l with s_l = H_l sigma / H (no mask, no median) -> waverec2 -> exp(y) - 1;
+ *   f = sigmoid((img - T) / crossover) (filtering.py:13-51);  out = fg_f f + bg_f (1 - f);  then `- dark` when
+ *   dark > 0, `/ flat` when flat != NULL, clip to [0, 65535], truncate to uint16.
+ * sigma_fg == sigma_bg: one band, no blend; a sigma of 0 leaves that band unfiltered (the image itself); both 0:
+ * only dark / flat / clip.  in / out: host or device pointers ([Z][H][W]); thresholds: host, one per plane;
+ * flat: host [H][W] or NULL; level < 0 = maximum level.  Needs 3 float32 planes of workspace per max_planes. */
+int dstr_dual_band_chunk(dstr_ctx* ctx, const void* in, int in_dtype, uint16_t* out, int Z, float sigma_fg,
+                         float sigma_bg, int level, const float* thresholds, float crossover, float dark,
+                         const float* flat);
+/* Exact histogram of every uint16 plane, hist[Z][65536] (host).  The host derives the dual-band threshold from it
+ * (skimage threshold_otsu on an integer image counts every value). */
+int dstr_histogram_u16(dstr_ctx* ctx, const uint16_t* in, int Z, uint32_t* hist);
 /* 1: the row filter (filtering.py:195-217) of every band 96 <= W_l <= 1056 runs on the 5th-generation
  * tensor cores (tcgen05.mma kind::f16 on fp16 hi/lo operand pairs, accumulators in TMEM, operands
  * staged by TMA bulk copies; csrc/dstr_notch_umma.cuh); 0 (default, or environment DSTR_UMMA=1 to flip
