@@ -238,4 +238,47 @@ int64_t dstr_blosc_decompress(const void* frame_, uint64_t frame_bytes, void* ds
     return (int64_t)nbytes;
 }
 
+// PNG row filters (PNG specification, section 9): `scan` holds h rows of (1 filter byte + stride data bytes) as they
+// come out of inflate; the reconstructed rows go to `out` (h * stride bytes).  bpp = bytes per complete pixel.
+// Used by the TIFF / PNG front-end (destriper.imread, reference readers.py:64-89 reads PNG through imageio).
+int dstr_png_unfilter(const uint8_t* scan, int h, int stride, int bpp, uint8_t* out) {
+    if (!scan || !out || h <= 0 || stride <= 0 || bpp <= 0) return DSTR_E_ARG;
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* in = scan + (size_t)y * (stride + 1);
+        const int ft = in[0];
+        ++in;
+        uint8_t* cur = out + (size_t)y * stride;
+        const uint8_t* up = y ? cur - stride : nullptr;
+        switch (ft) {
+            case 0:
+                std::memcpy(cur, in, stride);
+                break;
+            case 1:
+                for (int x = 0; x < stride; ++x) cur[x] = (uint8_t)(in[x] + (x >= bpp ? cur[x - bpp] : 0));
+                break;
+            case 2:
+                for (int x = 0; x < stride; ++x) cur[x] = (uint8_t)(in[x] + (up ? up[x] : 0));
+                break;
+            case 3:
+                for (int x = 0; x < stride; ++x) {
+                    const int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0;
+                    cur[x] = (uint8_t)(in[x] + ((a + b) >> 1));
+                }
+                break;
+            case 4:
+                for (int x = 0; x < stride; ++x) {
+                    const int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+                    const int p = a + b - c;
+                    const int pa = p > a ? p - a : a - p, pb = p > b ? p - b : b - p, pc = p > c ? p - c : c - p;
+                    const int pr = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                    cur[x] = (uint8_t)(in[x] + pr);
+                }
+                break;
+            default:
+                return DSTR_E_ARG;
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

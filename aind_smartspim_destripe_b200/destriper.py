@@ -9,8 +9,9 @@ same-shape images in batches of ``chunks`` planes to one GPU engine call.
 
 File formats: ``.raw`` (8-byte width/height header + uint16, either byte order) is built in;
 TIFF uses ``tifffile`` when it is importable and otherwise a minimal baseline codec
-(uncompressed, single-sample strips) that covers the SmartSPIM acquisition files; PNG needs
-``imageio`` like the reference.
+(uncompressed, single-sample strips) that covers the SmartSPIM acquisition files; PNG goes through
+``imageio`` like the reference when it is importable, else through a built-in codec (8 / 16-bit,
+non-interlaced; inflate in Python, row filters in the native library).
 """
 
 from __future__ import annotations
@@ -110,6 +111,73 @@ def _tiff_write(path: str, img: np.ndarray):
 
 
 # ---------------------------------------------------------------------------- readers.py mirror
+_PNG_SIG = b"\x89PNG\r\n\x1a\n"
+
+
+def _png_read(path) -> np.ndarray:
+    """Built-in PNG reader for the acquisition formats (8 / 16-bit greyscale, gray+alpha, RGB(A); non-interlaced):
+    chunk parsing and inflate here, row reconstruction in the native library (``dstr_png_unfilter``)."""
+    import ctypes as C
+    import zlib
+
+    from . import engine as _eng
+
+    with open(path, "rb") as fp:
+        buf = fp.read()
+    if buf[:8] != _PNG_SIG:
+        raise OSError(f"{path}: not a PNG file")
+    pos, idat, hdr = 8, [], None
+    while pos + 8 <= len(buf):
+        n, kind = struct.unpack(">I4s", buf[pos : pos + 8])
+        body = buf[pos + 8 : pos + 8 + n]
+        pos += 12 + n
+        if kind == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif kind == b"IDAT":
+            idat.append(body)
+        elif kind == b"IEND":
+            break
+    if hdr is None:
+        raise OSError(f"{path}: missing IHDR")
+    w, h, depth, ctype, _, _, interlace = hdr
+    channels = {0: 1, 2: 3, 4: 2, 6: 4}.get(ctype)
+    if channels is None or depth not in (8, 16) or interlace:
+        raise NotImplementedError(f"{path}: PNG colour type {ctype} / depth {depth} / interlace {interlace} is not supported without imageio")
+    bpp = channels * depth // 8
+    stride = w * bpp
+    scan = zlib.decompress(b"".join(idat))
+    if len(scan) != h * (stride + 1):
+        raise OSError(f"{path}: truncated PNG data")
+    out = np.empty(h * stride, dtype=np.uint8)
+    rc = _eng.load_library().dstr_png_unfilter(scan, h, stride, bpp, out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise OSError(f"{path}: bad PNG filter byte")
+    img = out.view(">u2").astype(np.uint16) if depth == 16 else out
+    return img.reshape(h, w) if channels == 1 else img.reshape(h, w, channels)
+
+
+def _png_write(path, img, compression=1):
+    """Greyscale 8 / 16-bit PNG (filter type 0, zlib level ``compression``)."""
+    import zlib
+
+    img = np.asarray(img)
+    if img.ndim != 2 or img.dtype not in (np.uint8, np.uint16):
+        raise NotImplementedError("the built-in PNG writer stores 2-D uint8 / uint16 images")
+    h, w = img.shape
+    depth = 8 * img.dtype.itemsize
+    rows = np.empty((h, 1 + w * img.dtype.itemsize), dtype=np.uint8)
+    rows[:, 0] = 0
+    rows[:, 1:] = img.astype(img.dtype.newbyteorder(">"), copy=False).view(np.uint8).reshape(h, -1)
+
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
+
+    data = _PNG_SIG + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, 0, 0, 0, 0))
+    data += chunk(b"IDAT", zlib.compress(rows.tobytes(), int(compression))) + chunk(b"IEND", b"")
+    with open(path, "wb") as fp:
+        fp.write(data)
+
+
 def raw_imread(path):
     """``.raw``: two uint32 (width, height) then uint16 pixels; endianness by the smaller width
     (reference readers.py:34-61; like there the array is shaped ``(width, height)``)."""
@@ -135,9 +203,7 @@ def imread(path: PathLike) -> np.ndarray:
     if ext in (".tif", ".tiff"):
         return _tifffile.imread(path) if _tifffile is not None else _tiff_read(path)
     if ext == ".png":
-        if _iio is None:
-            raise NotImplementedError("reading .png needs imageio (not installed)")
-        return _iio.imread(path)
+        return _iio.imread(path) if _iio is not None else _png_read(path)
     return None
 
 
@@ -160,9 +226,10 @@ def imsave(path, img, compression=1, output_format: Optional[str] = None):
         else:
             _tiff_write(target, img)
     else:
-        if _iio is None:
-            raise NotImplementedError("writing .png needs imageio (not installed)")
-        _iio.v3.imwrite(target, img, compress_level=compression)  # pragma: no cover
+        if _iio is not None:  # pragma: no cover
+            _iio.v3.imwrite(target, img, compress_level=compression)
+        else:
+            _png_write(target, img, compression)
 
 
 def _find_all_images(search_path: PathLike, input_path: PathLike, output_path: PathLike) -> List[Path]:

@@ -115,6 +115,7 @@ def load_library() -> C.CDLL:
                 [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, vp],
             ),
             "dstr_histogram_u16": (C.c_int, [vp, vp, C.c_int, vp]),
+            "dstr_png_unfilter": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
             "dstr_notch_umma_apply_host": (C.c_int, [C.c_int, C.c_double, C.c_double, dp, dp, ip]),
             "dstr_downscale2x": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
             "dstr_blosc_available": (C.c_int, [C.c_int]),
@@ -138,7 +139,7 @@ EXPORTED_SYMBOLS = (
     "dstr_compute_stream dstr_set_profiling dstr_get_timers dstr_reset_timers dstr_set_debug_stop "
     "dstr_debug_fetch dstr_set_subchunk dstr_set_overlap dstr_set_tma dstr_set_umma dstr_set_row_filter dstr_notch_umma_info "
     "dstr_notch_umma_apply_host dstr_downscale2x dstr_set_pyramid_outputs dstr_blosc_available dstr_blosc_compress "
-    "dstr_blosc_decompress dstr_dual_band_chunk dstr_histogram_u16"
+    "dstr_blosc_decompress dstr_dual_band_chunk dstr_histogram_u16 dstr_png_unfilter"
 ).split()
 
 

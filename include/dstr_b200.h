@@ -232,6 +232,10 @@ int dstr_blosc_available(int compressor);
 int64_t dstr_blosc_compress(const void* src, uint64_t nbytes, int typesize, int clevel, int shuffle, int compressor,
                             uint64_t blocksize, void* dst, uint64_t dst_capacity);
 int64_t dstr_blosc_decompress(const void* frame, uint64_t frame_bytes, void* dst, uint64_t dst_capacity);
+
+/* PNG row reconstruction (filter types 0-4) for the TIFF / PNG front-end (reference readers.py:64-89 reads PNG
+ * through imageio): scan = h rows of (1 filter byte + stride bytes) as inflated, out = h * stride bytes. */
+int dstr_png_unfilter(const uint8_t* scan, int h, int stride, int bpp, uint8_t* out);
 /* sub-chunk size (planes) used when streaming host buffers; 0 restores the default */
 int dstr_set_subchunk(dstr_ctx* ctx, int planes);
 

@@ -100,3 +100,60 @@ def test_cast_output_saturates():
     out = D._cast_output(np.array([-5.0, 10.7, 70000.0]), np.uint16)
     assert out.dtype == np.uint16 and list(out) == [0, 10, 65535]
     assert D._cast_output(np.array([1.5]), np.float32).dtype == np.float32
+
+
+def _png_filtered(img, filters):
+    """Encode a greyscale image with the given per-row PNG filter types (the spec's forward filters)."""
+    import zlib
+
+    h, w = img.shape
+    bpp = img.dtype.itemsize
+    raw = img.astype(img.dtype.newbyteorder(">")).view(np.uint8).reshape(h, -1).astype(np.int32)
+    rows = bytearray()
+    for y in range(h):
+        ft = filters[y % len(filters)]
+        cur = raw[y]
+        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        up = raw[y - 1] if y else np.zeros_like(cur)
+        ul = np.concatenate([np.zeros(bpp, np.int32), up[:-bpp]])
+        if ft == 0:
+            f = cur
+        elif ft == 1:
+            f = cur - left
+        elif ft == 2:
+            f = cur - up
+        elif ft == 3:
+            f = cur - ((left + up) >> 1)
+        else:
+            p = left + up - ul
+            pa, pb, pc = np.abs(p - left), np.abs(p - up), np.abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+            f = cur - pred
+        rows += bytes([ft]) + (f & 0xFF).astype(np.uint8).tobytes()
+
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
+
+    half = len(rows) // 2  # two IDAT chunks
+    z = zlib.compress(bytes(rows), 6)
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8 * bpp, 0, 0, 0, 0))
+            + chunk(b"IDAT", z[: len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2 :]) + chunk(b"IEND", b""))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_builtin_png_codec_all_row_filters(tmp_path, dtype):
+    """readers.py:64-89 reads PNG through imageio; without it the built-in codec must decode every filter type."""
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, np.iinfo(dtype).max, (37, 29)).astype(dtype)
+    img[5:20] = (np.arange(29) * 7).astype(dtype)[None, :]
+    p = tmp_path / "f.png"
+    p.write_bytes(_png_filtered(img, [0, 1, 2, 3, 4]))
+    out = D.imread(p)
+    assert out.dtype == dtype
+    np.testing.assert_array_equal(out, img)
+    q = tmp_path / "w.png"
+    D.imsave(str(q), img, compression=3, output_format=".png")
+    np.testing.assert_array_equal(D.imread(q), img)
+    (tmp_path / "bad.png").write_bytes(b"not a png")
+    with pytest.raises(OSError):
+        D.imread(tmp_path / "bad.png")
