@@ -12,6 +12,8 @@ What it restates (numpy + scipy.fftpack, dtype-faithful):
   ``:338-491`` (sigmoid .. filter_stripes)            -> ``oracle.plane_filter``
 * ``zarr_destriper.py:253-336`` (execute_worker)         -> ``oracle.worker``
 * PyWavelets==1.6.0 ``wavedec2/waverec2`` (not vendored) -> ``oracle.dwt``
+* pystripe ``filter_streaks`` / ``filter_subband`` (not in the snapshot;
+  SURVEY.md Appendix B)                                -> ``oracle.dual_band``
 * scikit-image==0.24.0 ``threshold_otsu`` on top of
   numpy==1.26.4 ``np.histogram`` semantics (not vendored)-> ``oracle.otsu``
 
@@ -21,6 +23,14 @@ re-hosted in ``tests/test_oracle_reference_kat.py``).  The DWT restatement is
 pinned by PyWavelets' documented known answers (db1/db2) and perfect
 reconstruction.  The *composition* pywt∘otsu∘fftpack inside
 ``log_space_fft_filtering`` is pinned by NO reference test or golden vector
-(the reference only asserts shape/positivity) and pywt/skimage are not
-installable here, so for that composition this oracle is **parity unpinned**.
+(the reference only asserts shape/positivity) and pywt/skimage are installable
+neither here nor on the GPU box (``profiles/r2_gpu_box_import_probe.txt``), so
+for that composition this oracle is **parity unpinned**.  What stands in for a
+reference-made vector is an independent second restatement that shares no code
+with this package (``tests/test_oracle_independent.py``: db3 taps from the
+spectral factorisation, ``scipy.signal.upfirdn`` DWT, OpenCV / brute-force
+Otsu, ``numpy.fft`` packed layout) and agrees with it to 1e-9.
+``oracle.dual_band`` (pystripe's classic dual-band mode) restates an algorithm
+that is not in the reference snapshot at all: **parity unpinned** by
+construction.
 """
