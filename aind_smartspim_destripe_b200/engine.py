@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -344,10 +345,14 @@ class DestripeEngine:
 
     def _ck(self, rc: int, what: str):
         if rc:
+            if not getattr(self, "ctx", None):
+                raise EngineError(f"{what}: this engine has been closed (get_engine evicts and closes engines; "
+                                  "do not keep one across calls of the functional API)")
             _raise(rc, self.ctx, what)
 
     # -- shadow correction fields --------------------------------------------------------------
     def set_flat_dark(self, flat: Optional[np.ndarray], dark: Optional[np.ndarray]):
+        self._shadow_key = None  # filtering._engine_with_shadow's cache describes what IT uploaded last
         if flat is None or dark is None:
             self._ck(self.lib.dstr_set_flat_dark(self.ctx, None, None), "dstr_set_flat_dark")
             self._flat_dark_key = None
@@ -562,8 +567,16 @@ class DestripeEngine:
         return out
 
 
+class _EngineCache(dict):
+    """dict that can be weakly referenced (and hashed by identity): the per-thread cache dies with its thread, and
+    its engines with it"""
+
+    __hash__ = object.__hash__
+    __eq__ = object.__eq__
+
+
 _tls = threading.local()  # per-thread engine cache (an engine is not thread-safe)
-_all_caches = []          # for release_engines()
+_all_caches = weakref.WeakSet()  # for release_engines(); weak, so caches of finished threads are collected
 _engines_lock = threading.Lock()
 _MAX_CACHED_ENGINES = 6   # each engine owns a device workspace proportional to max_planes * H * W
 
@@ -584,9 +597,9 @@ def get_engine(H: int, W: int, device: Optional[int] = None, max_planes: int = 1
         device = default_device()
     cache = getattr(_tls, "engines", None)
     if cache is None:
-        cache = _tls.engines = {}
+        cache = _tls.engines = _EngineCache()
         with _engines_lock:
-            _all_caches.append(cache)
+            _all_caches.add(cache)
     key = (int(device), int(H), int(W))
     eng = cache.pop(key, None)
     if eng is not None and eng.max_planes < max_planes:
@@ -603,7 +616,7 @@ def get_engine(H: int, W: int, device: Optional[int] = None, max_planes: int = 1
 def release_engines():
     """Close every cached engine (call only when no thread is inside the functional API)."""
     with _engines_lock:
-        for cache in _all_caches:
+        for cache in list(_all_caches):
             for eng in list(cache.values()):
                 eng.close()
             cache.clear()

@@ -224,15 +224,26 @@ def _resolve_shadow(shadow_correction: dict, input_tile_path, shape):
     return flatfield, darkfield, dark_c
 
 
+def _fingerprint(a) -> tuple:
+    """Cheap content mark of an array: 64 strided samples (an upload cache key, not a hash)."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    if flat.size == 0:
+        return (a.shape,)
+    step = max(1, flat.size // 64)
+    return (a.shape, str(a.dtype), flat[::step][:64].astype(np.float64).tobytes(), float(flat[-1]))
+
+
 def _engine_with_shadow(eng, shadow_correction, input_tile_path, shape):
     """Upload flat/dark once per (engine, flat array, dark array); the cache lives on the engine."""
     flat, dark_full, dark_c = _resolve_shadow(shadow_correction, input_tile_path, shape)
     cached = getattr(eng, "_shadow_key", None)
-    if cached is None or cached[0] is not flat or cached[1] is not dark_full:
+    mark = (_fingerprint(flat), _fingerprint(dark_full))  # catches in-place edits of the same arrays
+    if cached is None or cached[0] is not flat or cached[1] is not dark_full or cached[2] != mark:
         f32 = np.ascontiguousarray(flat, dtype=np.float32)
         d32 = np.ascontiguousarray(dark_c, dtype=np.float32)
-        eng.set_flat_dark(f32, d32)
-        eng._shadow_key = (flat, dark_full)  # holding the arrays keeps the identity test valid
+        eng.set_flat_dark(f32, d32)  # (resets eng._shadow_key)
+        eng._shadow_key = (flat, dark_full, mark)  # holding the arrays keeps the identity test valid
 
 
 def filter_planes(

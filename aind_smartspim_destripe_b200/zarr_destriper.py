@@ -579,6 +579,15 @@ def destripe_zarr(
                   "tile_config": tile_config}
 
     chunk_planes = int(prediction_chunksize[-3])
+    if len(prediction_chunksize) >= 3 and (int(prediction_chunksize[-2]) < H or int(prediction_chunksize[-1]) < W):
+        import warnings
+
+        warnings.warn(
+            f"prediction_chunksize {tuple(prediction_chunksize)} is smaller than the plane ({H}, {W}): the reference "
+            "would filter every YX block on its own (zarr_destriper.py:253-336); this driver always filters whole "
+            "planes, so the result differs from the reference's per-block output for this chunking",
+            stacklevel=2,
+        )
     # stream whole source chunks when that stays small: a 128-deep source chunk read 64 planes at a
     # time would be decoded twice
     src_cz = int(getattr(src, "chunks", (1, 1, chunk_planes))[2])
@@ -618,11 +627,19 @@ def destripe_zarr(
                     totals[k] += tm.get(k, 0.0)
             if not fused and n_levels > 1 and z1 > z0:
                 # float output (no shadow correction) or unusual chunking: levels from the written data
-                a0 = z0 - z0 % 4
-                prev = np.asarray(levels[0][t, c, a0:z1])
-                for k in range(1, n_levels):
-                    prev = compute_pyramid(prev, 2, [2, 2, 2])[-1]
-                    levels[k][t, c, (a0 >> k) : (a0 >> k) + prev.shape[0]] = prev[: max(0, shapes[k][2] - (a0 >> k))]
+                # (streamed in pieces of whole coarsest-level windows, so host memory stays at one piece)
+                win = 1 << (n_levels - 1)
+                a0 = z0 - z0 % win
+                piece = int(np.lcm(max(chunk_planes, 64), win))
+                for p0 in range(a0, z1, piece):
+                    prev = np.asarray(levels[0][t, c, p0 : min(z1, p0 + piece)])
+                    for k in range(1, n_levels):
+                        if prev.shape[0] < 2:
+                            break  # a trailing odd plane has no window at this level (floor semantics)
+                        prev = compute_pyramid(prev, 2, [2, 2, 2])[-1]
+                        room = max(0, shapes[k][2] - (p0 >> k))
+                        if prev.shape[0] and room:
+                            levels[k][t, c, (p0 >> k) : (p0 >> k) + min(room, prev.shape[0])] = prev[:room]
     for lv in levels:
         lv.close()
     if hasattr(src, "close"):

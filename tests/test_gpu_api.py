@@ -289,6 +289,18 @@ def test_destripe_zarr_tile_driver_matches_oracle(tmp_path, production_configs):
     assert attrs["multiscales"][0]["datasets"][1]["coordinateTransformations"][0]["scale"] == [1.0, 1.0, 4.0, 3.6, 3.6]
     assert json.loads((out / ".zgroup").read_text()) == {"zarr_format": 2}
 
+    # without a flat field there is no fused pyramid: the levels are built from the written level 0 in streamed
+    # pieces (64 + 8 planes here), and a YX chunking smaller than the plane is announced as a deviation
+    out_nf = tmp_path / "results_noflat" / "Ex_488_Em_525" / tile.name
+    with pytest.warns(UserWarning, match="smaller than the plane"):
+        zd.destripe_zarr(tile, "0", out_nf, (16, H // 2, W), 3072, 0, 1, None, tmp_path, tmp_path / "no_derivatives",
+                         [1.8, 1.8, 2.0], params, flatfield=None, compressor=None)
+    lv_nf = [zs.ZarrArray.open(out_nf / str(k)) for k in range(3)]
+    pyr_nf = OP.compute_pyramid(lv_nf[0][0, 0], 3, [2, 2, 2])
+    np.testing.assert_array_equal(lv_nf[1][0, 0], pyr_nf[1])
+    np.testing.assert_array_equal(lv_nf[2][0, 0], pyr_nf[2])
+    assert lv_nf[0][0, 0].any()
+
     # two "ranks" (run one after the other) write the same tile as one rank: slabs [0, 256) and [256, 320)
     Z2, H2, W2 = 320, 96, 112
     vol2 = S.synthetic_stack(Z2, H2, W2, base_seed=78, cells_every=5, n_unique=8)
