@@ -537,7 +537,8 @@ class DestripeEngine:
         self._ck(self.lib.dstr_set_tma(self.ctx, 1 if enabled else 0), "dstr_set_tma")
 
     def set_umma(self, enabled: bool):
-        """Row filter on the tcgen05 tensor-core kernel (default) or on the CUDA-core kernel."""
+        """Row filter on the tcgen05 / TMEM / TMA kernel (opt-in: parity-green but measured slower than the default
+        ``mma.sync`` kernel)."""
         self._ck(self.lib.dstr_set_umma(self.ctx, 1 if enabled else 0), "dstr_set_umma")
 
     def set_row_filter(self, kind: int):

@@ -151,6 +151,57 @@ def z_slab(n_planes: int, rank: int, world_size: int, align: int = 64) -> Tuple[
     return min(b0 * align, n_planes), min(b1 * align, n_planes)
 
 
+# Engine contexts + pinned staging buffers of destripe_volume, kept between calls: page-locking a few GB and creating
+# the contexts costs 2-3 s, several times the streaming time of a whole tile, and the tiles of a channel (or the
+# chunks of a benchmark) all have the same geometry.  At most `_POOL_MAX` idle sets are kept; `release_volume_resources`
+# (also registered with atexit) frees them.
+_pool_lock = threading.Lock()
+_pool: "dict[tuple, list]" = {}
+_POOL_MAX = 2
+
+
+def _pool_take(key):
+    with _pool_lock:
+        sets = _pool.get(key)
+        if sets:
+            return sets.pop()
+    return None
+
+
+def _free_resource_set(res):
+    for pb in res["in"] + res["out"] + [p for ps in res["pyr"] for p in ps]:
+        pb.free()
+    for e in res["engines"]:
+        e.close()
+
+
+def _pool_give(key, res):
+    evicted = []
+    with _pool_lock:
+        _pool.setdefault(key, []).append(res)
+        idle = [(k, r) for k, v in _pool.items() for r in v]
+        while len(idle) > _POOL_MAX:
+            k, r = idle.pop(0)  # oldest first (dict and list order)
+            _pool[k].remove(r)
+            evicted.append(r)
+    for r in evicted:
+        _free_resource_set(r)
+
+
+def release_volume_resources():
+    """Free the idle engine contexts / pinned buffers kept by ``destripe_volume(..., reuse_resources=True)``."""
+    with _pool_lock:
+        sets = [r for v in _pool.values() for r in v]
+        _pool.clear()
+    for r in sets:
+        _free_resource_set(r)
+
+
+import atexit as _atexit
+
+_atexit.register(release_volume_resources)
+
+
 def destripe_volume(
     volume,
     output,
@@ -166,6 +217,7 @@ def destripe_volume(
     pyramid_outputs: Optional[Sequence] = None,
     io_threads: int = 4,
     device_workers: int = 2,
+    reuse_resources: bool = True,
 ):
     """Stream ``volume[z0:z1]`` (array-like ``(Z, H, W)``, uint16 or float32) through the GPU.
 
@@ -181,6 +233,9 @@ def destripe_volume(
     on its Z-chunk boundaries, so no two threads ever touch the same stored chunk.
     ``device_workers``: engine contexts fed from the same queue (each call is synchronous in its own
     host thread), so the upload / kernels / download of consecutive chunks overlap.
+
+    ``reuse_resources``: keep the engine contexts and pinned buffers for the next call with the same geometry
+    (``release_volume_resources()`` frees them); ``setup_s`` / ``teardown_s`` of the returned dict show the cost.
 
     A failure in the reader, a device worker or the writer stops all of them and is re-raised here
     (the reference's consumers would hang on ``join``, zarr_destriper.py:1171).
@@ -342,17 +397,25 @@ def destripe_volume(
     try:
         # engine contexts and pinned buffers are created concurrently: page-locking GBs of host memory and the
         # first CUDA context / module load each take seconds when done one after the other
+        pool_key = (int(dev), int(H), int(W), int(chunk_planes), np.dtype(in_dtype).str, np.dtype(out_dtype).str,
+                    int(n_buf), int(device_workers), int(n_pyr))
+        pooled = _pool_take(pool_key) if reuse_resources else None
+        if pooled is not None:
+            engines, in_bufs, out_bufs, pyr_bufs = pooled["engines"], pooled["in"], pooled["out"], pooled["pyr"]
         with ThreadPoolExecutor(max(4, device_workers)) as setup:
-            f_eng = [setup.submit(_eng.DestripeEngine, H, W, min(chunk_planes, 16), dev) for _ in range(device_workers)]
-            f_in = [setup.submit(_eng.PinnedBuffer, (chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
-            f_out = [setup.submit(_eng.PinnedBuffer, (chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
-            f_pyr = [[setup.submit(_eng.PinnedBuffer, (max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
-                      for k in range(n_pyr)] for _ in range(n_buf)]
-            for f in f_eng:
-                engines.append(f.result())
-            in_bufs = [f.result() for f in f_in]
-            out_bufs = [f.result() for f in f_out]
-            pyr_bufs = [[f.result() for f in fs] for fs in f_pyr]
+            if pooled is not None:
+                setup = None
+            f_eng = [] if setup is None else [setup.submit(_eng.DestripeEngine, H, W, min(chunk_planes, 16), dev) for _ in range(device_workers)]
+            if setup is not None:
+                f_in = [setup.submit(_eng.PinnedBuffer, (chunk_planes, H, W), in_dtype) for _ in range(n_buf)]
+                f_out = [setup.submit(_eng.PinnedBuffer, (chunk_planes, H, W), out_dtype) for _ in range(n_buf)]
+                f_pyr = [[setup.submit(_eng.PinnedBuffer, (max(chunk_planes >> (k + 1), 1), H >> (k + 1), W >> (k + 1)), np.uint16)
+                          for k in range(n_pyr)] for _ in range(n_buf)]
+                for f in f_eng:
+                    engines.append(f.result())
+                in_bufs = [f.result() for f in f_in]
+                out_bufs = [f.result() for f in f_out]
+                pyr_bufs = [[f.result() for f in fs] for fs in f_pyr]
         for i in range(n_buf):
             free_in.put(i)
             free_out.put(i)
@@ -377,10 +440,15 @@ def destripe_volume(
         for pool in (rpool, wpool):
             if pool is not None:
                 pool.shutdown(wait=True)
-        for pb in in_bufs + out_bufs + [p for ps in pyr_bufs for p in ps]:
-            pb.free()
-        for e in engines:
-            e.close()
+        res = dict(engines=engines, **{"in": in_bufs, "out": out_bufs, "pyr": pyr_bufs})
+        complete = (len(engines) == device_workers and len(in_bufs) == n_buf and len(out_bufs) == n_buf)
+        if reuse_resources and not errors and complete and t_stream_end is not None:
+            for e in engines:
+                if n_pyr:
+                    e.set_pyramid_outputs(None, None)
+            _pool_give(pool_key, res)
+        else:
+            _free_resource_set(res)
         t_end = time.perf_counter()
         times["wall_s"] = t_end - t_wall
         if t_setup_end is not None and t_stream_end is not None:
