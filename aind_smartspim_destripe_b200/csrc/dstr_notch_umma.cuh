@@ -136,7 +136,10 @@ template <unsigned SLEEP_NS>
 __device__ __forceinline__ void um_wait_ns(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = um_smem_u32(bar);
     uint32_t done;
-    for (;;) {
+    // watchdog: a launch of this kernel takes a few milliseconds; a wait that lasts seconds means a lost arrival
+    // (a bug), and a trap that fails the launch is better than a kernel that never returns
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -146,6 +149,12 @@ __device__ __forceinline__ void um_wait_ns(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (done) break;
         if (SLEEP_NS) __nanosleep(SLEEP_NS);
+        if ((spins & 0x3ffu) == 0x3ffu) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();  // 4 s
+        }
     }
 }
 __device__ __forceinline__ void um_wait(uint64_t* bar, uint32_t parity) { um_wait_ns<1000>(bar, parity); }

@@ -101,3 +101,46 @@ def test_expm1_flag_and_f32_output():
     b = eng.filter_chunk(img[None], p, out_dtype=np.float32, flags=E.FLAG_EXPM1)
     np.testing.assert_allclose(a - b, 2.0, atol=1e-2)  # exp(y) + 1 (reference) vs exp(y) - 1 (corrected)
     eng.close()
+
+
+def _degenerate_planes(H, W):
+    rng = np.random.default_rng(11)
+    step = np.full((H, W), 200, np.uint16)
+    step[:, W // 2 :] = 4000
+    hot = np.full((H, W), 300, np.uint16)
+    hot[H // 3, W // 5] = 65535
+    rows = (100 + 50 * (np.arange(H) % 7)).astype(np.uint16)[:, None].repeat(W, 1)  # pure horizontal streaks
+    return {
+        "all zero": np.zeros((H, W), np.uint16),
+        "constant 1000": np.full((H, W), 1000, np.uint16),
+        "saturated": np.full((H, W), 65535, np.uint16),
+        "vertical step": step,
+        "one hot pixel": hot,
+        "streaks only": rows,
+        "full-range noise": rng.integers(0, 65536, (H, W)).astype(np.uint16),
+        "binary 0 / 65535": (rng.integers(0, 2, (H, W)) * 65535).astype(np.uint16),
+    }
+
+
+@pytest.mark.parametrize("name", list(_degenerate_planes(8, 8)))
+def test_degenerate_planes_match_the_oracle(name, production_configs):
+    """Constant, saturated, binary and single-outlier planes: zero-width histograms (threshold_otsu returns the
+    value itself), empty masks, all-masked rows, log(1 + 65535) at the top of the range."""
+    no_cells, cells = production_configs
+    H, W = 192, 256
+    img = _degenerate_planes(H, W)[name]
+    flat, dark = S.synthetic_flat_dark(H, W)
+    shadow = dict(retrospective=True, flatfield=flat, darkfield=dark, tile_config=None)
+    ref = OF.filter_stripes(img.astype(np.float32), "0_0", no_cells, cells, shadow, 2500)
+    out = fl.filter_stripes(img, "0_0", no_cells, cells, shadow, 2500)
+    assert out.dtype == np.uint16 and np.all(np.isfinite(out.astype(np.float64)))
+    frac, mx, exact = u16_agreement(out, ref)
+    print(f"{name}: within+-1 {frac:.6f} exact {exact:.4f} max abs {mx}")
+    assert frac >= U16_FRACTION
+    # and the float path (no shadow dict): finite, within tolerance
+    ref_f = OF.log_space_fft_filtering(img.astype(np.float32), **no_cells)
+    out_f = fl.log_space_fft_filtering(img.astype(np.float32), **no_cells)
+    assert np.all(np.isfinite(out_f))
+    e = rel_err(out_f, ref_f)
+    print(f"{name}: float rel {e:.2e}")
+    assert e < 10 * REL_TOL

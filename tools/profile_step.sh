@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --csv --log-file gpurun_out/${TAG}_launches_bench_steps2_c2.csv python bench.py --steps 2 --warmup 1 --no-extra \
     > gpurun_out/ncu_list.log 2>&1
 python bench.py --steps 2 --warmup 1 --no-extra > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:filter_rows_mma -s 8 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:filter_rows_mma -s 21 -c 1 \
     -o gpurun_out/${TAG}_rows_mma_L1 -f python bench.py --steps 2 --warmup 1 --no-extra > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_list.log gpurun_out/ncu_full.log
 cat gpurun_out/${TAG}_bench_c2.json
