@@ -840,6 +840,11 @@ int launch_filter(dstr_ctx* ctx, const FilterLevelArgs& fa, int Z, size_t smem, 
 }
 
 // Everything one chunk pass needs to launch its kernels.
+// The row-filter kernels load a row as EPL x 32 lanes without a bounds test (EPL = template width >= ceil(W_l / 32)): the
+// over-read of the last row of the last plane must stay inside the allocation.  Largest template: 65 (tcgen05: 33).
+constexpr int kHSlack = 32 * 65 + 32;
+static_assert(kHSlack >= 32 * 65, "row-filter over-read slack");
+
 constexpr int kModeForceCells = 2;  // internal: every plane uses the `cells` tables (second band of the dual-band mode)
 
 struct Pass {
@@ -1097,6 +1102,10 @@ int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
                         8 * (size_t)std::max(FR_ROWS * ra.Jpad_max, 4) + 2 * (size_t)FR_ROWS * 2 * (ra.Jpad_max + 8) +
                         4 * (size_t)FR_ROWS * (epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65);
     if (smem > 227 * 1024 || epl > 65) return -1000;
+    {
+        const int tmpl = epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65;
+        if (32 * tmpl > g.W + kHSlack) return fail(ctx, DSTR_E_STATE, "row-filter over-read exceeds the band slack");
+    }
     if (epl <= 2) return launch_rows_mma<2>(ctx, ra, P.z, smem, P.dp, st);
     if (epl <= 5) return launch_rows_mma<5>(ctx, ra, P.z, smem, P.dp, st);
     if (epl <= 9) return launch_rows_mma<9>(ctx, ra, P.z, smem, P.dp, st);
@@ -1480,7 +1489,7 @@ int dstr_create(int device, int max_planes, int H, int W, dstr_ctx** out) {
         // slack: the synthesis kernel reads columns m+1, m+2 unconditionally (8 floats), the row filter
         // loads whole 32-lane groups of a row for a templated element count (up to 32 x 65 floats past the last row start)
         CKC(cudaMalloc(&ctx->d_A[l], sizeof(float) * (g.pstride * max_planes + 8)));
-        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + 2112)));  // 32 x 65 + 32
+        CKC(cudaMalloc(&ctx->d_H[l], sizeof(float) * (g.pstride * max_planes + kHSlack)));
     }
     if (ctx->Lalloc > 0) CKC(cudaMalloc(&ctx->d_lstat, sizeof(LevelStat) * (size_t)ctx->Lalloc * max_planes));
     CKC(cudaMalloc(&ctx->d_pstat, sizeof(PlaneStat) * (size_t)max_planes));

@@ -15,6 +15,7 @@
 // of a row are summed in the accumulator registers.  fp32 accumulation.  Thread (g, tig) of a warp ends
 // up with the outputs t0 + g and t0 + g + 8 of row tig.
 #pragma once
+#include <type_traits>
 #include "dstr_kernels.cuh"
 
 namespace dstr {
@@ -381,12 +382,15 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     const __half* ocol = s_O + g * a.len_o + 2 * tig;
     // every warp owns a contiguous range of segments (sizes differ by at most one)
     const int seg_lo = (a.nseg16 * wid) / FR_ROWS, seg_hi = (a.nseg16 * (wid + 1)) / FR_ROWS;
-    for (int sg0 = seg_lo; sg0 < seg_hi; sg0 += RM_SG) {
-        const int cnt = min(RM_SG, seg_hi - sg0);
-        float acc[RM_SG][4];
-        float ye[RM_SG][2];
+    // One group of G consecutive segments, G a compile-time constant: full groups of RM_SG share the tap fragments of a
+    // k step; the 0..RM_SG-1 leftover segments of a warp run as groups of one.  (A run-time count would put every
+    // mma.sync under a predicate, which costs a WARPSYNC + NOP per MMA.)
+    auto do_group = [&](auto Gc, const int sg0) {
+        constexpr int G = decltype(Gc)::value;
+        float acc[G][4];
+        float ye[G][2];
 #pragma unroll
-        for (int i = 0; i < RM_SG; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int i = 0; i < G; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
         if (mc.J > 0) {
             const int ktiles = mc.Jpad >> 4;
             const __half* ccol = s_ch + g * chs + 2 * tig;
@@ -394,19 +398,17 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 const unsigned b0 = *reinterpret_cast<const unsigned*>(ccol + 16 * kt);
                 const unsigned b1 = *reinterpret_cast<const unsigned*>(ccol + 16 * kt + 8);
 #pragma unroll
-                for (int i = 0; i < RM_SG; ++i) {
+                for (int i = 0; i < G; ++i) {
                     const int seg = sg0 + i;
-                    if (i < cnt) {
-                        const uint4* tf = mc.T2f + ((size_t)seg * ktiles + kt) * 64 + 2 * lane;
-                        const uint4 fh = __ldg(tf), fl = __ldg(tf + 1);
-                        const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
-                        mma_f16(acc[i], ah, b0, b1);
-                        mma_f16(acc[i], al, b0, b1);
-                    }
+                    const uint4* tf = mc.T2f + ((size_t)seg * ktiles + kt) * 64 + 2 * lane;
+                    const uint4 fh = __ldg(tf), fl = __ldg(tf + 1);
+                    const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
+                    mma_f16(acc[i], ah, b0, b1);
+                    mma_f16(acc[i], al, b0, b1);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < RM_SG; ++i)
+            for (int i = 0; i < G; ++i)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[i][k] *= x_to_f;
         }
@@ -421,19 +423,16 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
             al[2] = *reinterpret_cast<const unsigned*>(tel + 16 * s + 8);
             al[3] = al[0];
 #pragma unroll
-            for (int i = 0; i < RM_SG; ++i) {
-                const int seg = sg0 + i;
-                if (i < cnt) {
-                    const __half* xc = ecol + 16 * (seg + s);
-                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
-                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
-                    mma_f16(acc[i], ah, b0, b1);
-                    mma_f16(acc[i], al, b0, b1);
-                }
+            for (int i = 0; i < G; ++i) {
+                const __half* xc = ecol + 16 * (sg0 + i + s);
+                const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
+                const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
+                mma_f16(acc[i], ah, b0, b1);
+                mma_f16(acc[i], al, b0, b1);
             }
         }
 #pragma unroll
-        for (int i = 0; i < RM_SG; ++i) {
+        for (int i = 0; i < G; ++i) {
             ye[i][0] = acc[i][0] + acc[i][1];
             ye[i][1] = acc[i][2] + acc[i][3];
             acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -449,22 +448,18 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
             al[2] = *reinterpret_cast<const unsigned*>(tol + 16 * s + 8);
             al[3] = al[0];
 #pragma unroll
-            for (int i = 0; i < RM_SG; ++i) {
-                const int seg = sg0 + i;
-                if (i < cnt) {
-                    const __half* xc = ocol + 16 * (seg + s);
-                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
-                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
-                    mma_f16(acc[i], ah, b0, b1);
-                    mma_f16(acc[i], al, b0, b1);
-                }
+            for (int i = 0; i < G; ++i) {
+                const __half* xc = ocol + 16 * (sg0 + i + s);
+                const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
+                const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
+                mma_f16(acc[i], ah, b0, b1);
+                mma_f16(acc[i], al, b0, b1);
             }
         }
-        if (!rvalid) continue;
+        if (!rvalid) return;
         // dH[t] = masked ? 0 : -(B x)[t];  (B x)[t] = y_e + y_o,  (B x)[n - t] = y_e - y_o
 #pragma unroll
-        for (int i = 0; i < RM_SG; ++i) {
-            if (i >= cnt) break;
+        for (int i = 0; i < G; ++i) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int t = 16 * (sg0 + i) + g + 8 * h;
@@ -480,7 +475,10 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 }
             }
         }
-    }
+    };
+    int sg0 = seg_lo;
+    for (; sg0 + RM_SG <= seg_hi; sg0 += RM_SG) do_group(std::integral_constant<int, RM_SG>{}, sg0);
+    for (; sg0 < seg_hi; ++sg0) do_group(std::integral_constant<int, 1>{}, sg0);
 }
 
 }  // namespace dstr
