@@ -90,6 +90,14 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(a.pitch * 4) : "memory");
         }
     }
+    // the row of this warp, requested before anything else: the DRAM / L2 latency of these loads runs under the
+    // table copies below (a warp past the end of the band reads the last row again and drops it)
+    unsigned key[EPL];
+    {
+        const float* gl = a.cH + (size_t)z * a.pstride + (size_t)(row0 + min(wid, nrows - 1)) * a.pitch + lane;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) key[i] = __float_as_uint(gl[32 * i]);
+    }
     const int cfgi = plane_uses_cells(pstat[z], dp);
     const MmaCfg mc = cfgi ? a.cfg[1] : a.cfg[0];
     const LevelStat* st = a.lstat + (size_t)z * a.stat_stride;
@@ -126,12 +134,6 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     if (wid < nrows) {
         const float* grow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + wid) * a.pitch;
         // ---- load, mask, keys (see filter_rows_kernel) --------------------------------------------
-        unsigned key[EPL];
-        {
-            const float* gl = grow + lane;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) key[i] = __float_as_uint(gl[32 * i]);
-        }
         // fp16 images of the scaled zero-filled row, two per register (+inf past the end): the median search below
         // does its first, coarse bisection on these with packed compares (any rounding is monotone, so the order
         // statistics of the images bracket those of the floats)
