@@ -256,7 +256,8 @@ analysis_kernel(const IN_T* __restrict__ in, int Hs, int Ws, int in_pitch, size_
     __shared__ double s_dred[2][AN_WARPS];
     __shared__ unsigned s_cred[2][AN_WARPS];
 
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction: the tile test below is no divergence
     const int z = blockIdx.z;
     const int ox0 = (blockIdx.x * AN_WX + (wid % AN_WX)) * AN_OXW;
     const int oy0 = (blockIdx.y * AN_WY + (wid / AN_WX)) * AN_TOY;

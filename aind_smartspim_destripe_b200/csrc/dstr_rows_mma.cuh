@@ -77,7 +77,8 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     __half* s_ch = reinterpret_cast<__half*>(s_c64 + max(FR_ROWS * a.Jpad_max, 4));  // [FR_ROWS * 2][chs]
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_ch + FR_ROWS * 2 * chs);        // [FR_ROWS][EPL]
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // same value, but known to be warp-uniform: no divergence handling
     const int z = blockIdx.y;
     const int row0 = blockIdx.x * FR_ROWS;
     const int nrows = min(FR_ROWS, a.Hl - row0);
