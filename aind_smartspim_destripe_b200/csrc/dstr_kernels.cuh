@@ -1032,7 +1032,8 @@ filter_rows_kernel(FilterLevelArgs a, const PlaneStat* __restrict__ pstat, Dispa
     const int cstride = a.Jpad_max + 8;  // rows 8 banks apart: the 4 rows' c_j are read in one wavefront
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_c + FR_ROWS * cstride);                            // [FR_ROWS][EPL] mask bits
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
 #ifdef DSTR_ABLATION
     const int abl = a.ablate;
 #else
@@ -1579,7 +1580,7 @@ synth_kernel(const float* __restrict__ dA, const float* __restrict__ dH, int Hl,
              size_t pstride_l, float* __restrict__ outA, int Ho, int Wo, int pitch_o,
              size_t pstride_o, const IN_T* __restrict__ img, OUT_T* __restrict__ out,
              size_t img_pstride, EpilogueArgs ep) {
-    const int wid = threadIdx.x >> 5;
+    const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
     const int x0 = (blockIdx.x * SY_WARPS + wid) * SY_TX;
     const int y0 = blockIdx.y * SY_TY;
     if (x0 >= Wo) return;  // no block-level synchronisation below
