@@ -584,6 +584,7 @@ void build_umma_host(int n, double s, const UmmaGeom& g, UmmaHost& out) {
 // ---- tables of the mma.sync row filter (dstr_rows_mma.cuh) from the hybrid design -------------
 struct MmaHost {
     std::vector<uint16_t> tr;    // [E: hi0 | hi1 | lo0 | lo1][trlen_e], [O: ...][trlen_o]
+    std::vector<uint32_t> fq;    // tap fragments as register quads: [E: S_e][hi, lo][14][4], [O: S_o][hi, lo][14][4]
     std::vector<uint16_t> T1f;   // [nblk][Jpad / 16][32][16 halfs: 8 hi, 8 lo]
     std::vector<uint16_t> T2f;   // [nseg16][Jpad / 16][32][16 halfs]
     MmaCfg cfg = {};
@@ -620,6 +621,24 @@ void build_mma_host(int n, const NotchHost& h, MmaHost& out) {
     };
     fill_tr(0, c.trlen_e, c.ntap_e, h.te, h.ntap_e);
     fill_tr((size_t)4 * c.trlen_e, c.trlen_o, c.ntap_o, h.to, h.ntap_o);
+    // the same taps as the register quads the kernel loads: lane (g, tig) reads q = 2 tig - g + 15 (8 .. 21)
+    out.fq.assign((size_t)(c.S_e + c.S_o) * 28 * 4, 0u);
+    auto fill_fq = [&](size_t qbase, size_t trbase, int trlen, int S) {
+        for (int s = 0; s < S; ++s)
+            for (int part = 0; part < 2; ++part) {
+                const uint16_t* t = out.tr.data() + trbase + (size_t)(part ? 2 : 0) * trlen;  // unshifted hi / lo copy
+                auto w = [&](int i) -> uint32_t { return (uint32_t)t[i] | ((uint32_t)t[i + 1] << 16); };
+                for (int q = 8; q <= 21; ++q) {
+                    uint32_t* dst = out.fq.data() + (qbase + ((size_t)s * 2 + part) * 14 + (q - 8)) * 4;
+                    dst[0] = w(16 * s + q);
+                    dst[1] = w(16 * s + q - 8);
+                    dst[2] = w(16 * s + q + 8);
+                    dst[3] = dst[0];
+                }
+            }
+    };
+    fill_fq(0, 0, c.trlen_e, c.S_e);
+    fill_fq((size_t)c.S_e * 28, (size_t)4 * c.trlen_e, c.trlen_o, c.S_o);
     c.J = h.J;
     c.Jpad = pad16(h.J);
     c.cs = 1.0f;
@@ -736,7 +755,9 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
         }
         auto pad256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
         const size_t b_tr = pad256(mh.tr.size() * 2), b_t1 = pad256(mh.T1f.size() * 2), b_t2 = pad256(mh.T2f.size() * 2);
-        CK(ctx, cudaMalloc(&D.d_mma, b_tr + b_t1 + b_t2 + 256));
+        const size_t b_fq = pad256(mh.fq.size() * 4);
+        CK(ctx, cudaMalloc(&D.d_mma, b_tr + b_t1 + b_t2 + b_fq + 256));
+        CK(ctx, cudaMemcpyAsync(D.d_mma + b_tr + b_t1 + b_t2, mh.fq.data(), mh.fq.size() * 4, cudaMemcpyHostToDevice, ctx->s_comp));
         CK(ctx, cudaMemcpyAsync(D.d_mma, mh.tr.data(), mh.tr.size() * 2, cudaMemcpyHostToDevice, ctx->s_comp));
         if (!mh.T1f.empty())
             CK(ctx, cudaMemcpyAsync(D.d_mma + b_tr, mh.T1f.data(), mh.T1f.size() * 2, cudaMemcpyHostToDevice, ctx->s_comp));
@@ -747,6 +768,7 @@ int build_taps_cfg(dstr_ctx* ctx, int level, int cfg, float sigma) {
         D.mm.tr = reinterpret_cast<const __half*>(D.d_mma);
         D.mm.T1f = reinterpret_cast<const uint4*>(D.d_mma + b_tr);
         D.mm.T2f = reinterpret_cast<const uint4*>(D.d_mma + b_tr + b_t1);
+        D.mm.fq = reinterpret_cast<const uint4*>(D.d_mma + b_tr + b_t1 + b_t2);
     }
     {
         const UmmaGeom g = umma_geom(n);
@@ -1092,13 +1114,15 @@ int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
     ra.trlen_e_max = std::max(ra.cfg[0].trlen_e, ra.cfg[1].trlen_e);
     ra.trlen_o_max = std::max(ra.cfg[0].trlen_o, ra.cfg[1].trlen_o);
     ra.Jpad_max = std::max(ra.cfg[0].Jpad, ra.cfg[1].Jpad);
+    ra.S_e_max = std::max(ra.cfg[0].S_e, ra.cfg[1].S_e);
+    ra.S_o_max = std::max(ra.cfg[0].S_o, ra.cfg[1].S_o);
     {
         static const int pf = (int)env_or("DSTR_FILTER_PREFETCH", -1.0);
         ra.prefetch_blocks = pf >= 0 ? pf : 8 * ctx->sm_count;
         if ((g.pitch * 4) % 16 != 0) ra.prefetch_blocks = 0;
     }
     const int epl = (g.W + 31) / 32;
-    const size_t smem = 2 * ((size_t)4 * ra.trlen_e_max + 4 * ra.trlen_o_max + (size_t)FR_ROWS * 2 * (ra.len_e + ra.len_o)) +
+    const size_t smem = (size_t)16 * 28 * (ra.S_e_max + ra.S_o_max) + 2 * ((size_t)FR_ROWS * 2 * (ra.len_e + ra.len_o)) +
                         8 * (size_t)std::max(FR_ROWS * ra.Jpad_max, 4) + 2 * (size_t)FR_ROWS * 2 * (ra.Jpad_max + 8) +
                         4 * (size_t)FR_ROWS * (epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65);
     if (smem > 227 * 1024 || epl > 65) return -1000;

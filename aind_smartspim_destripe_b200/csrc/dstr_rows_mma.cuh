@@ -22,6 +22,7 @@ namespace dstr {
 
 struct MmaCfg {
     const __half* tr;   // reversed tap tables [E: hi0 | hi1 | lo0 | lo1] (trlen_e each) then [O: ...] (trlen_o each)
+    const uint4* fq;    // tap A fragments as whole register quads: [E: S_e][hi, lo][14][4 words] then [O: S_o][hi, lo][14][4]
     const uint4* T1f;   // [nblk][Jpad / 16][32 lanes][hi, lo]  A fragments of T1 (modes x 16 elements)
     const uint4* T2f;   // [nseg16][Jpad / 16][32 lanes][hi, lo] A fragments of T2 (16 outputs x 16 modes)
     int ntap_e, ue_lo, ntap_o, uo_lo;  // tap counts padded to 16; tap k <-> circular offset u = u?_lo + k
@@ -44,6 +45,7 @@ struct RowsMmaArgs {
     int nseg16;     // 16-output segments
     int len_e, len_o;  // halfs per (row, part) operand array (max over the configs; = 8 mod 64)
     int trlen_e_max, trlen_o_max, Jpad_max;
+    int S_e_max, S_o_max;
     int prefetch_blocks;
 };
 
@@ -68,9 +70,12 @@ __global__ void __launch_bounds__(FR_THREADS, (EPL <= 33 ? DSTR_RM_MINB : 4))
 filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.Wl;
-    __half* s_tre = reinterpret_cast<__half*>(smem_raw);           // [4][trlen_e_max]
-    __half* s_tro = s_tre + 4 * a.trlen_e_max;                      // [4][trlen_o_max]
-    __half* s_E = s_tro + 4 * a.trlen_o_max;                        // [FR_ROWS * 2][len_e]
+    // tap fragments: entry (s, part, q - 8) is the register quad {t[16 s + q], t[16 s + q - 8], t[16 s + q + 8], t[16 s + q]}
+    // (half pairs of the reversed, pre-scaled tap table) that a lane with q = 2 tig - g + 15 feeds to the MMA as
+    // operand A of k step s — one 16-byte shared-memory load per fragment, nothing to assemble in registers
+    uint4* s_fqe = reinterpret_cast<uint4*>(smem_raw);              // [S_e_max][2][14]
+    uint4* s_fqo = s_fqe + a.S_e_max * 28;                          // [S_o_max][2][14]
+    __half* s_E = reinterpret_cast<__half*>(s_fqo + a.S_o_max * 28);  // [FR_ROWS * 2][len_e]
     __half* s_O = s_E + FR_ROWS * 2 * a.len_e;                      // [FR_ROWS * 2][len_o]
     unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * 2 * a.len_o);  // [FR_ROWS][Jpad_max]
     const int chs = a.Jpad_max + 8;                                 // c operand stride: = 8 (mod 16) halfs
@@ -117,17 +122,9 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     }
     const int nh = a.nh;
 
-    // tap tables of this plane's config -> shared memory
-    {
-        const unsigned* src = reinterpret_cast<const unsigned*>(mc.tr);
-        unsigned* de = reinterpret_cast<unsigned*>(s_tre);
-        unsigned* dO = reinterpret_cast<unsigned*>(s_tro);
-        for (int c = 0; c < 4; ++c) {
-            for (int i = tid; i < mc.trlen_e / 2; i += FR_THREADS) de[c * (a.trlen_e_max / 2) + i] = src[c * (mc.trlen_e / 2) + i];
-            for (int i = tid; i < mc.trlen_o / 2; i += FR_THREADS)
-                dO[c * (a.trlen_o_max / 2) + i] = src[2 * mc.trlen_e + c * (mc.trlen_o / 2) + i];
-        }
-    }
+    // tap fragments of this plane's config -> shared memory
+    for (int i = tid; i < mc.S_e * 28; i += FR_THREADS) s_fqe[i] = __ldg(mc.fq + i);
+    for (int i = tid; i < mc.S_o * 28; i += FR_THREADS) s_fqo[i] = __ldg(mc.fq + mc.S_e * 28 + i);
     for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS) s_c64[i] = 0ull;
 
     const int OFFe = mc.ue_lo + mc.ntap_e, OFFo = mc.uo_lo + mc.ntap_o;
@@ -370,13 +367,9 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // of the even part and is rescaled (a power of two) into the units of the FIR before the taps are added.
     const float inv_f = 1.0f / (scale * RM_TAP_SCALE);
     const float x_to_f = mc.inv_x * RM_TAP_SCALE;  // (1 / (cs ts)) / (1 / 256)
-    // q = 16 s + 2 tig - g + 15 indexes the reversed tap table; lanes with an odd q read the copy shifted by one
-    const int q0 = 2 * tig - g + 15;
-    const int odd = q0 & 1;
-    const __half* teh = s_tre + (odd ? a.trlen_e_max : 0) - odd + q0;
-    const __half* tel = s_tre + (odd ? 3 : 2) * a.trlen_e_max - odd + q0;
-    const __half* toh = s_tro + (odd ? a.trlen_o_max : 0) - odd + q0;
-    const __half* tol = s_tro + (odd ? 3 : 2) * a.trlen_o_max - odd + q0;
+    // q = 2 tig - g + 15 selects the lane's fragment of a k step
+    const uint4* fqe = s_fqe + (2 * tig - g + 15 - 8);
+    const uint4* fqo = s_fqo + (2 * tig - g + 15 - 8);
     const int r = tig;  // the row whose outputs this thread ends up with
     const bool rvalid = r < nrows;
     float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + (rvalid ? r : 0)) * a.pitch;
@@ -416,15 +409,8 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
                 for (int k = 0; k < 4; ++k) acc[i][k] *= x_to_f;
         }
         for (int s = 0; s < mc.S_e; ++s) {
-            unsigned ah[4], al[4];
-            ah[0] = *reinterpret_cast<const unsigned*>(teh + 16 * s);
-            ah[1] = *reinterpret_cast<const unsigned*>(teh + 16 * s - 8);
-            ah[2] = *reinterpret_cast<const unsigned*>(teh + 16 * s + 8);
-            ah[3] = ah[0];
-            al[0] = *reinterpret_cast<const unsigned*>(tel + 16 * s);
-            al[1] = *reinterpret_cast<const unsigned*>(tel + 16 * s - 8);
-            al[2] = *reinterpret_cast<const unsigned*>(tel + 16 * s + 8);
-            al[3] = al[0];
+            const uint4 fh = fqe[s * 28], fl = fqe[s * 28 + 14];
+            const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
 #pragma unroll
             for (int i = 0; i < G; ++i) {
                 const __half* xc = ecol + 16 * (sg0 + i + s);
@@ -441,15 +427,8 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
             acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
         }
         for (int s = 0; s < mc.S_o; ++s) {
-            unsigned ah[4], al[4];
-            ah[0] = *reinterpret_cast<const unsigned*>(toh + 16 * s);
-            ah[1] = *reinterpret_cast<const unsigned*>(toh + 16 * s - 8);
-            ah[2] = *reinterpret_cast<const unsigned*>(toh + 16 * s + 8);
-            ah[3] = ah[0];
-            al[0] = *reinterpret_cast<const unsigned*>(tol + 16 * s);
-            al[1] = *reinterpret_cast<const unsigned*>(tol + 16 * s - 8);
-            al[2] = *reinterpret_cast<const unsigned*>(tol + 16 * s + 8);
-            al[3] = al[0];
+            const uint4 fh = fqo[s * 28], fl = fqo[s * 28 + 14];
+            const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
 #pragma unroll
             for (int i = 0; i < G; ++i) {
                 const __half* xc = ocol + 16 * (sg0 + i + s);
