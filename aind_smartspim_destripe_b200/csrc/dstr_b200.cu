@@ -344,7 +344,7 @@ double notch_cost_j() {
     return v;
 }
 double notch_cost_jpad() {
-    static const double v = env_or("DSTR_NOTCH_COST_JPAD", 2.0);
+    static const double v = env_or("DSTR_NOTCH_COST_JPAD", 0.5);
     return v;
 }
 
@@ -1104,9 +1104,9 @@ int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
     ra.cfg[1] = T.cfg[1].mm;
     ra.nh = g.W / 2;
     ra.nseg16 = (ra.nh + 1 + 15) / 16;
-    auto len_of = [&](int S) {  // entries the MMAs read, padded so that (len / 2) = 4 (mod 32): conflict-free operand loads
-        int len = 16 * ra.nseg16 + 16 * S;
-        len += (8 - len % 64 + 64) % 64;
+    auto len_of = [&](int S) {  // entries the MMAs read, padded so that (len / 2) = 4 (mod 8) words: the 8 operand columns of a
+        int len = 16 * ra.nseg16 + 16 * S;  // warp start 4 * odd banks apart, i.e. on 8 different 4-bank groups (conflict-free)
+        len += (8 - len % 16 + 16) % 16;
         return len;
     };
     ra.len_e = len_of(std::max(ra.cfg[0].S_e, ra.cfg[1].S_e));
@@ -1122,9 +1122,11 @@ int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
         if ((g.pitch * 4) % 16 != 0) ra.prefetch_blocks = 0;
     }
     const int epl = (g.W + 31) / 32;
-    const size_t smem = (size_t)16 * 28 * (ra.S_e_max + ra.S_o_max) + 2 * ((size_t)FR_ROWS * 2 * (ra.len_e + ra.len_o)) +
+    size_t smem = (size_t)16 * 28 * (ra.S_e_max + ra.S_o_max) + 2 * ((size_t)FR_ROWS * 2 * (ra.len_e + ra.len_o)) +
                         8 * (size_t)std::max(FR_ROWS * ra.Jpad_max, 4) + 2 * (size_t)FR_ROWS * 2 * (ra.Jpad_max + 8) +
                         4 * (size_t)FR_ROWS * (epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65);
+    static const size_t extra_smem = (size_t)env_or("DSTR_RM_EXTRA_SMEM", 0.0);  // occupancy experiments
+    smem += extra_smem;
     if (smem > 227 * 1024 || epl > 65) return -1000;
     {
         const int tmpl = epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65;

@@ -43,7 +43,7 @@ struct RowsMmaArgs {
     MmaCfg cfg[2];  // [0] no_cells, [1] cells
     int nh;         // n / 2: outputs t = 0 .. nh
     int nseg16;     // 16-output segments
-    int len_e, len_o;  // halfs per (row, part) operand array (max over the configs; = 8 mod 64)
+    int len_e, len_o;  // halfs per (row, part) operand array (max over the configs; = 8 mod 16)
     int trlen_e_max, trlen_o_max, Jpad_max;
     int S_e_max, S_o_max;
     int prefetch_blocks;
