@@ -1,4 +1,4 @@
-"""Emulation of the two-stage row median of dstr_rows_mma.cuh (coarse bisection on fp16 images of the scaled values,
+"""Emulation (numpy) of the two-stage row median of csrc/dstr_rows_mma.cuh (coarse bisection on fp16 images of the scaled values,
 exact finish on the float keys) against np.median of the zero-filled row."""
 import numpy as np
 
