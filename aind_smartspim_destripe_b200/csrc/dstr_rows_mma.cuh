@@ -291,33 +291,57 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
             __half* El = Eh + a.len_e;
             __half* Oh = s_O + (wid * 2) * a.len_o;
             __half* Ol = Oh + a.len_o;
-            const int tau_lo = -max(OFFe, OFFo);
+            // two consecutive entries per lane and step: the E pair is one aligned half2 store per part (the first
+            // entry of a pair is even); the O pair too when OFFo - OFFe is even, else four 16-bit stores
+            int tau_lo = -max(OFFe, OFFo);
+            tau_lo -= (tau_lo + OFFe) & 1;
             const int tau_hi = max(use_e - OFFe, use_o - OFFo);
-            int t = (tau_lo + lane) % n;
-            if (t < 0) t += n;
-            const int step = 32 % n;
+            const bool o_aligned = ((OFFo - OFFe) & 1) == 0;
+            int t0 = (tau_lo + 2 * lane) % n;
+            if (t0 < 0) t0 += n;
+            const int step = 64 % n;
             const float* gp = grow;
             asm volatile("" : "+l"(gp));
             const float hs = 0.5f * scale;
-            int ae = tau_lo + lane + OFFe, ao = tau_lo + lane + OFFo;
-            for (int tau = tau_lo + lane; tau < tau_hi; tau += 32, ae += 32, ao += 32) {
-                const unsigned tr = (t == 0) ? 0u : (unsigned)(n - t);
-                const float c1 = gp[(unsigned)t], c2 = gp[tr];
-                const float x1 = (__fmul_rn(c1, c1) > thr_q) ? med : c1;
-                const float x2 = (__fmul_rn(c2, c2) > thr_q) ? med : c2;
-                const float ve = hs * (x1 + x2), vo = hs * (x1 - x2);
-                if ((unsigned)ae < (unsigned)use_e) {
-                    const __half h = __float2half_rn(ve);
-                    Eh[ae] = h;
-                    El[ae] = __float2half_rn(ve - __half2float(h));
+            int ae = tau_lo + 2 * lane + OFFe, ao = tau_lo + 2 * lane + OFFo;
+            for (int tau = tau_lo + 2 * lane; tau < tau_hi; tau += 64, ae += 64, ao += 64) {
+                const int t1 = (t0 + 1 == n) ? 0 : t0 + 1;
+                const unsigned m0 = (t0 == 0) ? 0u : (unsigned)(n - t0), m1 = (t1 == 0) ? 0u : (unsigned)(n - t1);
+                const float c00 = gp[(unsigned)t0], c01 = gp[(unsigned)t1], c10 = gp[m0], c11 = gp[m1];
+                const float x00 = (__fmul_rn(c00, c00) > thr_q) ? med : c00;
+                const float x01 = (__fmul_rn(c01, c01) > thr_q) ? med : c01;
+                const float x10 = (__fmul_rn(c10, c10) > thr_q) ? med : c10;
+                const float x11 = (__fmul_rn(c11, c11) > thr_q) ? med : c11;
+                const float ve0 = hs * (x00 + x10), vo0 = hs * (x00 - x10);
+                const float ve1 = hs * (x01 + x11), vo1 = hs * (x01 - x11);
+                if ((unsigned)ae < (unsigned)use_e) {  // ae and use_e are even: ae + 1 is in range as well
+                    const __half2 h = __floats2half2_rn(ve0, ve1);
+                    const float2 back = __half22float2(h);
+                    *reinterpret_cast<__half2*>(Eh + ae) = h;
+                    *reinterpret_cast<__half2*>(El + ae) = __floats2half2_rn(ve0 - back.x, ve1 - back.y);
                 }
-                if ((unsigned)ao < (unsigned)use_o) {
-                    const __half h = __float2half_rn(vo);
-                    Oh[ao] = h;
-                    Ol[ao] = __float2half_rn(vo - __half2float(h));
+                {
+                    const __half2 h = __floats2half2_rn(vo0, vo1);
+                    const float2 back = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(vo0 - back.x, vo1 - back.y);
+                    if (o_aligned) {
+                        if ((unsigned)ao < (unsigned)use_o) {
+                            *reinterpret_cast<__half2*>(Oh + ao) = h;
+                            *reinterpret_cast<__half2*>(Ol + ao) = l;
+                        }
+                    } else {
+                        if ((unsigned)ao < (unsigned)use_o) {
+                            Oh[ao] = __low2half(h);
+                            Ol[ao] = __low2half(l);
+                        }
+                        if ((unsigned)(ao + 1) < (unsigned)use_o) {
+                            Oh[ao + 1] = __high2half(h);
+                            Ol[ao + 1] = __high2half(l);
+                        }
+                    }
                 }
-                t += step;
-                if (t >= n) t -= n;
+                t0 += step;
+                if (t0 >= n) t0 -= n;
             }
         }
     }
