@@ -1067,7 +1067,7 @@ int launch_filter_umma(const Pass& P, int l, cudaStream_t st) {
     return rc;
 }
 
-template <int EPL>
+template <int EPL, int NT>
 int launch_rows_mma(dstr_ctx* ctx, const RowsMmaArgs& ra, int Z, size_t smem, const DispatchParams& dp, cudaStream_t st) {
     static std::mutex mtx;
     static bool done[64] = {};
@@ -1075,12 +1075,13 @@ int launch_rows_mma(dstr_ctx* ctx, const RowsMmaArgs& ra, int Z, size_t smem, co
         std::lock_guard<std::mutex> lk(mtx);
         const int dev = ctx->device & 63;
         if (!done[dev]) {
-            CK(ctx, cudaFuncSetAttribute(filter_rows_mma_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(ctx, cudaFuncSetAttribute(filter_rows_mma_kernel<EPL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             done[dev] = true;
         }
     }
-    dim3 grid((ra.Hl + FR_ROWS - 1) / FR_ROWS, Z);
-    filter_rows_mma_kernel<EPL><<<grid, FR_THREADS, smem, st>>>(ra, ctx->d_pstat, dp);
+    constexpr int rows = 4 * NT;
+    dim3 grid((ra.Hl + rows - 1) / rows, Z);
+    filter_rows_mma_kernel<EPL, NT><<<grid, 32 * rows, smem, st>>>(ra, ctx->d_pstat, dp);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     return 0;
@@ -1116,28 +1117,38 @@ int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
     ra.Jpad_max = std::max(ra.cfg[0].Jpad, ra.cfg[1].Jpad);
     ra.S_e_max = std::max(ra.cfg[0].S_e, ra.cfg[1].S_e);
     ra.S_o_max = std::max(ra.cfg[0].S_o, ra.cfg[1].S_o);
+    const int epl = (g.W + 31) / 32;
+    const int tmpl = epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65;
+    if (epl > 65) return -1000;
+    if (32 * tmpl > g.W + kHSlack) return fail(ctx, DSTR_E_STATE, "row-filter over-read exceeds the band slack");
+    auto smem_of = [&](int rows) {
+        return (size_t)16 * 28 * (ra.S_e_max + ra.S_o_max) + 2 * ((size_t)rows * 2 * (ra.len_e + ra.len_o)) +
+               8 * (size_t)std::max(rows * ra.Jpad_max, 4) + 2 * (size_t)rows * 2 * (ra.Jpad_max + 8) + 4 * (size_t)rows * tmpl;
+    };
+    static const size_t extra_smem = (size_t)env_or("DSTR_RM_EXTRA_SMEM", 0.0);  // occupancy experiments
+    // 8 rows per block (two n8 tiles per A fragment) while at least two blocks fit an SM; DSTR_RM_ROWS=4 forces the 4-row form
+    static const int force_rows = (int)env_or("DSTR_RM_ROWS", 0.0);
+    const int nt = (force_rows == 4 || smem_of(8) + extra_smem > 110 * 1024 || g.H < 8) ? 1 : 2;
+    const size_t smem = smem_of(4 * nt) + extra_smem;
+    if (smem > 227 * 1024) return -1000;
     {
+        // L2 prefetch one wave of resident blocks ahead; DSTR_FILTER_PREFETCH overrides (0 = off)
         static const int pf = (int)env_or("DSTR_FILTER_PREFETCH", -1.0);
-        ra.prefetch_blocks = pf >= 0 ? pf : 8 * ctx->sm_count;
+        ra.prefetch_blocks = pf >= 0 ? pf : (8 / nt) * ctx->sm_count;
         if ((g.pitch * 4) % 16 != 0) ra.prefetch_blocks = 0;
     }
-    const int epl = (g.W + 31) / 32;
-    size_t smem = (size_t)16 * 28 * (ra.S_e_max + ra.S_o_max) + 2 * ((size_t)FR_ROWS * 2 * (ra.len_e + ra.len_o)) +
-                        8 * (size_t)std::max(FR_ROWS * ra.Jpad_max, 4) + 2 * (size_t)FR_ROWS * 2 * (ra.Jpad_max + 8) +
-                        4 * (size_t)FR_ROWS * (epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65);
-    static const size_t extra_smem = (size_t)env_or("DSTR_RM_EXTRA_SMEM", 0.0);  // occupancy experiments
-    smem += extra_smem;
-    if (smem > 227 * 1024 || epl > 65) return -1000;
-    {
-        const int tmpl = epl <= 2 ? 2 : epl <= 5 ? 5 : epl <= 9 ? 9 : epl <= 17 ? 17 : epl <= 33 ? 33 : 65;
-        if (32 * tmpl > g.W + kHSlack) return fail(ctx, DSTR_E_STATE, "row-filter over-read exceeds the band slack");
-    }
-    if (epl <= 2) return launch_rows_mma<2>(ctx, ra, P.z, smem, P.dp, st);
-    if (epl <= 5) return launch_rows_mma<5>(ctx, ra, P.z, smem, P.dp, st);
-    if (epl <= 9) return launch_rows_mma<9>(ctx, ra, P.z, smem, P.dp, st);
-    if (epl <= 17) return launch_rows_mma<17>(ctx, ra, P.z, smem, P.dp, st);
-    if (epl <= 33) return launch_rows_mma<33>(ctx, ra, P.z, smem, P.dp, st);
-    return launch_rows_mma<65>(ctx, ra, P.z, smem, P.dp, st);
+#define RM_DISPATCH(E)                                                        \
+    do {                                                                      \
+        if (nt == 2) return launch_rows_mma<E, 2>(ctx, ra, P.z, smem, P.dp, st); \
+        return launch_rows_mma<E, 1>(ctx, ra, P.z, smem, P.dp, st);           \
+    } while (0)
+    if (tmpl == 2) RM_DISPATCH(2);
+    if (tmpl == 5) RM_DISPATCH(5);
+    if (tmpl == 9) RM_DISPATCH(9);
+    if (tmpl == 17) RM_DISPATCH(17);
+    if (tmpl == 33) RM_DISPATCH(33);
+    RM_DISPATCH(65);
+#undef RM_DISPATCH
 }
 
 int launch_filter_level(const Pass& P, int l, cudaStream_t st) {

@@ -65,9 +65,14 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const unsigned (&a)[4], u
 #ifndef DSTR_RM_MINB
 #define DSTR_RM_MINB 8
 #endif
-template <int EPL>
-__global__ void __launch_bounds__(FR_THREADS, (EPL <= 33 ? DSTR_RM_MINB : 4))
+// NT = n8 tiles of the operand matrices: a block filters ROWS = 4 NT rows (one warp each for the selection / operand
+// phase) and every A fragment — tap quads from shared memory, rank-J table fragments from L2 — feeds NT MMAs.  NT = 2
+// halves the table traffic per row (0.29 ms of the 1.87 ms row filter were those loads with NT = 1).
+template <int EPL, int NT>
+__global__ void __launch_bounds__(128 * NT, (EPL <= 33 ? DSTR_RM_MINB / NT : 4 / NT))
 filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
+    constexpr int ROWS = 4 * NT, THREADS = 32 * ROWS;
+    constexpr int GF = RM_SG / NT;  // segments per full group: NT GF accumulator tiles per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.Wl;
     // tap fragments: entry (s, part, q - 8) is the register quad {t[16 s + q], t[16 s + q - 8], t[16 s + q + 8], t[16 s + q]}
@@ -75,22 +80,22 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // operand A of k step s — one 16-byte shared-memory load per fragment, nothing to assemble in registers
     uint4* s_fqe = reinterpret_cast<uint4*>(smem_raw);              // [S_e_max][2][14]
     uint4* s_fqo = s_fqe + a.S_e_max * 28;                          // [S_o_max][2][14]
-    __half* s_E = reinterpret_cast<__half*>(s_fqo + a.S_o_max * 28);  // [FR_ROWS * 2][len_e]
-    __half* s_O = s_E + FR_ROWS * 2 * a.len_e;                      // [FR_ROWS * 2][len_o]
-    unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + FR_ROWS * 2 * a.len_o);  // [FR_ROWS][Jpad_max]
+    __half* s_E = reinterpret_cast<__half*>(s_fqo + a.S_o_max * 28);  // [ROWS * 2][len_e]
+    __half* s_O = s_E + ROWS * 2 * a.len_e;                      // [ROWS * 2][len_o]
+    unsigned long long* s_c64 = reinterpret_cast<unsigned long long*>(s_O + ROWS * 2 * a.len_o);  // [ROWS][Jpad_max]
     const int chs = a.Jpad_max + 8;                                 // c operand stride: = 8 (mod 16) halfs
-    __half* s_ch = reinterpret_cast<__half*>(s_c64 + max(FR_ROWS * a.Jpad_max, 4));  // [FR_ROWS * 2][chs]
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_ch + FR_ROWS * 2 * chs);        // [FR_ROWS][EPL]
+    __half* s_ch = reinterpret_cast<__half*>(s_c64 + max(ROWS * a.Jpad_max, 4));  // [ROWS * 2][chs]
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_ch + ROWS * 2 * chs);        // [ROWS][EPL]
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // same value, but known to be warp-uniform: no divergence handling
     const int z = blockIdx.y;
-    const int row0 = blockIdx.x * FR_ROWS;
-    const int nrows = min(FR_ROWS, a.Hl - row0);
+    const int row0 = blockIdx.x * ROWS;
+    const int nrows = min(ROWS, a.Hl - row0);
     if (a.prefetch_blocks > 0 && lane == 0) {  // rows of the block that will run in this slot one wave later: DRAM -> L2
         const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_blocks;
         const int pz = (int)(lin / gridDim.x);
-        const int prow = (int)(lin - (long long)pz * gridDim.x) * FR_ROWS + wid;
+        const int prow = (int)(lin - (long long)pz * gridDim.x) * ROWS + wid;
         if (pz < (int)gridDim.y && prow < a.Hl) {
             const float* pp = a.cH + (size_t)pz * a.pstride + (size_t)prow * a.pitch;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(a.pitch * 4) : "memory");
@@ -123,9 +128,9 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     const int nh = a.nh;
 
     // tap fragments of this plane's config -> shared memory
-    for (int i = tid; i < mc.S_e * 28; i += FR_THREADS) s_fqe[i] = __ldg(mc.fq + i);
-    for (int i = tid; i < mc.S_o * 28; i += FR_THREADS) s_fqo[i] = __ldg(mc.fq + mc.S_e * 28 + i);
-    for (int i = tid; i < FR_ROWS * a.Jpad_max; i += FR_THREADS) s_c64[i] = 0ull;
+    for (int i = tid; i < mc.S_e * 28; i += THREADS) s_fqe[i] = __ldg(mc.fq + i);
+    for (int i = tid; i < mc.S_o * 28; i += THREADS) s_fqo[i] = __ldg(mc.fq + mc.S_e * 28 + i);
+    for (int i = tid; i < ROWS * a.Jpad_max; i += THREADS) s_c64[i] = 0ull;
 
     const int OFFe = mc.ue_lo + mc.ntap_e, OFFo = mc.uo_lo + mc.ntap_o;
     const int use_e = 16 * a.nseg16 + 16 * mc.S_e, use_o = 16 * a.nseg16 + 16 * mc.S_o;  // operand entries the MMAs read
@@ -351,30 +356,39 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // ---- rank-J coefficients  c_j = sum_v T1[v][j] x_e[v]  (scaled like the operands) ------------
     if (mc.J > 0) {
         const int mtiles = mc.Jpad >> 4;
-        const int bw = (mc.nblk + FR_ROWS - 1) / FR_ROWS;
+        const int bw = (mc.nblk + ROWS - 1) / ROWS;
         const int b_begin = wid * bw, b_end = min(mc.nblk, b_begin + bw);
-        const __half* xcol = s_E + g * a.len_e + 16 * mc.blk_lo + 2 * tig;  // column g = (row g >> 1, part g & 1)
+        const __half* xcol = s_E + g * a.len_e + 16 * mc.blk_lo + 2 * tig;  // column 8 t + g = (row 4 t + (g >> 1), part g & 1)
         for (int mt = 0; mt < mtiles; ++mt) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[NT][4];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
             const uint4* tf = mc.T1f + ((size_t)b_begin * mtiles + mt) * 64 + 2 * lane;
             for (int blk = b_begin; blk < b_end; ++blk) {
                 const uint4 fh = __ldg(tf), fl = __ldg(tf + 1);
-                const unsigned b0 = *reinterpret_cast<const unsigned*>(xcol + 16 * blk);
-                const unsigned b1 = *reinterpret_cast<const unsigned*>(xcol + 16 * blk + 8);
                 const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
-                mma_f16(acc, ah, b0, b1);
-                mma_f16(acc, al, b0, b1);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xcol + 8 * t * a.len_e + 16 * blk);
+                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xcol + 8 * t * a.len_e + 16 * blk + 8);
+                    mma_f16(acc[t], ah, b0, b1);
+                    mma_f16(acc[t], al, b0, b1);
+                }
                 tf += (size_t)mtiles * 64;
             }
-            // acc[0] + acc[1]: mode 16 mt + g of row tig (hi and lo operand columns); acc[2] + acc[3]: mode + 8.
+            // acc[0] + acc[1]: mode 16 mt + g of row 4 t + tig (hi and lo operand columns); acc[2] + acc[3]: mode + 8.
             // Partial sums of the warps are combined as 2^-24 fixed point (order-free integer adds: deterministic)
             if (b_begin < b_end) {
-                atomicAdd(s_c64 + tig * a.Jpad_max + 16 * mt + g, (unsigned long long)__float2ll_rn((acc[0] + acc[1]) * 16777216.0f));
-                atomicAdd(s_c64 + tig * a.Jpad_max + 16 * mt + g + 8, (unsigned long long)__float2ll_rn((acc[2] + acc[3]) * 16777216.0f));
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    unsigned long long* dst = s_c64 + (4 * t + tig) * a.Jpad_max + 16 * mt + g;
+                    atomicAdd(dst, (unsigned long long)__float2ll_rn((acc[t][0] + acc[t][1]) * 16777216.0f));
+                    atomicAdd(dst + 8, (unsigned long long)__float2ll_rn((acc[t][2] + acc[t][3]) * 16777216.0f));
+                }
             }
         }
         __syncthreads();
-        for (int i = tid; i < FR_ROWS * mc.Jpad; i += FR_THREADS) {
+        for (int i = tid; i < ROWS * mc.Jpad; i += THREADS) {
             const int r = i / mc.Jpad, j = i - r * mc.Jpad;
             const float c = __ll2float_rn((long long)s_c64[r * a.Jpad_max + j]) * (1.0f / 16777216.0f) * mc.cs;
             const __half h = __float2half_rn(c);
@@ -394,96 +408,118 @@ filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, Dispa
     // q = 2 tig - g + 15 selects the lane's fragment of a k step
     const uint4* fqe = s_fqe + (2 * tig - g + 15 - 8);
     const uint4* fqo = s_fqo + (2 * tig - g + 15 - 8);
-    const int r = tig;  // the row whose outputs this thread ends up with
-    const bool rvalid = r < nrows;
-    float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + (rvalid ? r : 0)) * a.pitch;
-    const unsigned* mrow = s_mask + (rvalid ? r : 0) * EPL;
-    const __half* ecol = s_E + g * a.len_e + 2 * tig;  // operand column g = (row g >> 1, part g & 1)
+    // the rows whose outputs this thread ends up with: 4 t + tig
+    const __half* ecol = s_E + g * a.len_e + 2 * tig;  // operand column 8 t + g = (row 4 t + (g >> 1), part g & 1)
     const __half* ocol = s_O + g * a.len_o + 2 * tig;
     // every warp owns a contiguous range of segments (sizes differ by at most one)
-    const int seg_lo = (a.nseg16 * wid) / FR_ROWS, seg_hi = (a.nseg16 * (wid + 1)) / FR_ROWS;
-    // One group of G consecutive segments, G a compile-time constant: full groups of RM_SG share the tap fragments of a
-    // k step; the 0..RM_SG-1 leftover segments of a warp run as groups of one.  (A run-time count would put every
-    // mma.sync under a predicate, which costs a WARPSYNC + NOP per MMA.)
+    const int seg_lo = (a.nseg16 * wid) / ROWS, seg_hi = (a.nseg16 * (wid + 1)) / ROWS;
+    // One group of G consecutive segments, G a compile-time constant: full groups of GF share the tap fragments of a
+    // k step; the leftover segments of a warp run as groups of one.  (A run-time count would put every mma.sync
+    // under a predicate, which costs a WARPSYNC + NOP per MMA.)
     auto do_group = [&](auto Gc, const int sg0) {
         constexpr int G = decltype(Gc)::value;
-        float acc[G][4];
-        float ye[G][2];
+        float acc[G][NT][4];
+        float ye[G][NT][2];
 #pragma unroll
-        for (int i = 0; i < G; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[i][t][0] = acc[i][t][1] = acc[i][t][2] = acc[i][t][3] = 0.f;
         if (mc.J > 0) {
             const int ktiles = mc.Jpad >> 4;
             const __half* ccol = s_ch + g * chs + 2 * tig;
             for (int kt = 0; kt < ktiles; ++kt) {
-                const unsigned b0 = *reinterpret_cast<const unsigned*>(ccol + 16 * kt);
-                const unsigned b1 = *reinterpret_cast<const unsigned*>(ccol + 16 * kt + 8);
+                unsigned b0[NT], b1[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    b0[t] = *reinterpret_cast<const unsigned*>(ccol + 8 * t * chs + 16 * kt);
+                    b1[t] = *reinterpret_cast<const unsigned*>(ccol + 8 * t * chs + 16 * kt + 8);
+                }
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
                     const int seg = sg0 + i;
                     const uint4* tf = mc.T2f + ((size_t)seg * ktiles + kt) * 64 + 2 * lane;
                     const uint4 fh = __ldg(tf), fl = __ldg(tf + 1);
                     const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
-                    mma_f16(acc[i], ah, b0, b1);
-                    mma_f16(acc[i], al, b0, b1);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        mma_f16(acc[i][t], ah, b0[t], b1[t]);
+                        mma_f16(acc[i][t], al, b0[t], b1[t]);
+                    }
                 }
             }
 #pragma unroll
             for (int i = 0; i < G; ++i)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] *= x_to_f;
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[i][t][k] *= x_to_f;
         }
         for (int s = 0; s < mc.S_e; ++s) {
             const uint4 fh = fqe[s * 28], fl = fqe[s * 28 + 14];
             const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                const __half* xc = ecol + 16 * (sg0 + i + s);
-                const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
-                const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
-                mma_f16(acc[i], ah, b0, b1);
-                mma_f16(acc[i], al, b0, b1);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const __half* xc = ecol + 8 * t * a.len_e + 16 * (sg0 + i + s);
+                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
+                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
+                    mma_f16(acc[i][t], ah, b0, b1);
+                    mma_f16(acc[i][t], al, b0, b1);
+                }
             }
         }
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            ye[i][0] = acc[i][0] + acc[i][1];
-            ye[i][1] = acc[i][2] + acc[i][3];
-            acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        }
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                ye[i][t][0] = acc[i][t][0] + acc[i][t][1];
+                ye[i][t][1] = acc[i][t][2] + acc[i][t][3];
+                acc[i][t][0] = acc[i][t][1] = acc[i][t][2] = acc[i][t][3] = 0.f;
+            }
         for (int s = 0; s < mc.S_o; ++s) {
             const uint4 fh = fqo[s * 28], fl = fqo[s * 28 + 14];
             const unsigned ah[4] = {fh.x, fh.y, fh.z, fh.w}, al[4] = {fl.x, fl.y, fl.z, fl.w};
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                const __half* xc = ocol + 16 * (sg0 + i + s);
-                const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
-                const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
-                mma_f16(acc[i], ah, b0, b1);
-                mma_f16(acc[i], al, b0, b1);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const __half* xc = ocol + 8 * t * a.len_o + 16 * (sg0 + i + s);
+                    const unsigned b0 = *reinterpret_cast<const unsigned*>(xc);
+                    const unsigned b1 = *reinterpret_cast<const unsigned*>(xc + 8);
+                    mma_f16(acc[i][t], ah, b0, b1);
+                    mma_f16(acc[i][t], al, b0, b1);
+                }
             }
         }
-        if (!rvalid) return;
         // dH[t] = masked ? 0 : -(B x)[t];  (B x)[t] = y_e + y_o,  (B x)[n - t] = y_e - y_o
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
+        for (int tl = 0; tl < NT; ++tl) {
+            const int r = 4 * tl + tig;
+            if (r >= nrows) continue;
+            float* orow = a.cH + (size_t)z * a.pstride + (size_t)(row0 + r) * a.pitch;
+            const unsigned* mrow = s_mask + r * EPL;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = 16 * (sg0 + i) + g + 8 * h;
-                if (t > nh) continue;
-                const float yev = ye[i][h] * inv_f;
-                const float yo = (acc[i][2 * h] + acc[i][2 * h + 1]) * inv_f;
-                const bool md = (mrow[t >> 5] >> (t & 31)) & 1u;
-                orow[t] = md ? 0.f : -(yev + yo);
-                const int tm = n - t;
-                if (t >= 1 && tm != t) {
-                    const bool mm = (mrow[tm >> 5] >> (tm & 31)) & 1u;
-                    orow[tm] = mm ? 0.f : -(yev - yo);
+            for (int i = 0; i < G; ++i) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = 16 * (sg0 + i) + g + 8 * h;
+                    if (t > nh) continue;
+                    const float yev = ye[i][tl][h] * inv_f;
+                    const float yo = (acc[i][tl][2 * h] + acc[i][tl][2 * h + 1]) * inv_f;
+                    const bool md = (mrow[t >> 5] >> (t & 31)) & 1u;
+                    orow[t] = md ? 0.f : -(yev + yo);
+                    const int tm = n - t;
+                    if (t >= 1 && tm != t) {
+                        const bool mm = (mrow[tm >> 5] >> (tm & 31)) & 1u;
+                        orow[tm] = mm ? 0.f : -(yev - yo);
+                    }
                 }
             }
         }
     };
     int sg0 = seg_lo;
-    for (; sg0 + RM_SG <= seg_hi; sg0 += RM_SG) do_group(std::integral_constant<int, RM_SG>{}, sg0);
+    for (; sg0 + GF <= seg_hi; sg0 += GF) do_group(std::integral_constant<int, GF>{}, sg0);
     for (; sg0 < seg_hi; ++sg0) do_group(std::integral_constant<int, 1>{}, sg0);
 }
 
