@@ -205,12 +205,12 @@ int dstr_histogram_u16(dstr_ctx* ctx, const uint16_t* in, int Z, uint32_t* hist)
 /* 1: the row filter (filtering.py:195-217) of every band 96 <= W_l <= 1056 runs on the 5th-generation
  * tensor cores (tcgen05.mma kind::f16 on fp16 hi/lo operand pairs, accumulators in TMEM, operands
  * staged by TMA bulk copies; csrc/dstr_notch_umma.cuh); 0 (default, or environment DSTR_UMMA=1 to flip
- * it): the CUDA-core kernel, which measures 6-10 % faster on B200.  Both paths
- * pass the same parity tests. */
+ * it): the mma.sync kernel below, which measures 40 % faster on B200 (1.14 vs 1.93 ms for the level-1 launch of a
+ * 128 x 2048 x 2048 chunk; DESIGN.md section 5b explains why).  Both paths pass the same parity tests. */
 int dstr_set_umma(dstr_ctx* ctx, int enabled);
-/* CUDA-core row filter variant: 1 (default; environment DSTR_ROW_FILTER) = the even / odd FIRs and the rank-J
- * correction as mma.sync m16n8k16 products on fp16 hi/lo operand pairs (csrc/dstr_rows_mma.cuh), 0 = the
- * register-tiled FMA kernel of round 1.  Same operator tables, same parity tests. */
+/* Row filter variant when dstr_set_umma is off: 1 (default; environment DSTR_ROW_FILTER) = the even / odd FIRs and the
+ * rank-J correction as mma.sync m16n8k16 products on fp16 hi/lo operand pairs, 8 rows per block
+ * (csrc/dstr_rows_mma.cuh), 0 = the register-tiled FMA kernel of round 1.  Same operator design, same parity tests. */
 int dstr_set_row_filter(dstr_ctx* ctx, int kind);
 /* geometry of the tensor-core row filter for a band of width n:
  * info = {eligible, passes, outputs per pass, k chunks, table bytes, shared memory bytes, outputs, padded K}
