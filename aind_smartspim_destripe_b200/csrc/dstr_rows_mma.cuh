@@ -72,7 +72,7 @@ template <int EPL, int NT>
 __global__ void __launch_bounds__(128 * NT, (EPL <= 33 ? DSTR_RM_MINB / NT : 4 / NT))
 filter_rows_mma_kernel(RowsMmaArgs a, const PlaneStat* __restrict__ pstat, DispatchParams dp) {
     constexpr int ROWS = 4 * NT, THREADS = 32 * ROWS;
-    constexpr int GF = RM_SG / NT;  // segments per full group: NT GF accumulator tiles per thread
+    constexpr int GF = RM_SG;  // segments per full group (NT GF accumulator tiles per thread; measured: 4 beats 2 and 3 for NT = 2)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.Wl;
     // tap fragments: entry (s, part, q - 8) is the register quad {t[16 s + q], t[16 s + q - 8], t[16 s + q + 8], t[16 s + q]}
