@@ -1128,7 +1128,7 @@ int launch_filter_rows_mma(const Pass& P, int l, cudaStream_t st) {
     static const size_t extra_smem = (size_t)env_or("DSTR_RM_EXTRA_SMEM", 0.0);  // occupancy experiments
     // 8 rows per block (two n8 tiles per A fragment) while at least two blocks fit an SM; DSTR_RM_ROWS=4 forces the 4-row form
     static const int force_rows = (int)env_or("DSTR_RM_ROWS", 0.0);
-    const int nt = (force_rows == 4 || smem_of(8) + extra_smem > 110 * 1024 || g.H < 8) ? 1 : 2;
+    const int nt = (force_rows == 4 || ctx->row_filter == 2 || smem_of(8) + extra_smem > 110 * 1024 || g.H < 8) ? 1 : 2;
     const size_t smem = smem_of(4 * nt) + extra_smem;
     if (smem > 227 * 1024) return -1000;
     {
@@ -1157,7 +1157,7 @@ int launch_filter_level(const Pass& P, int l, cudaStream_t st) {
         const int rcu = launch_filter_umma(P, l, st);
         if (rcu != -1000) return rcu;
     }
-    if (ctx->row_filter == 1) {
+    if (ctx->row_filter >= 1) {
         const int rcm = launch_filter_rows_mma(P, l, st);
         if (rcm != -1000) return rcm;
     }
@@ -2056,7 +2056,7 @@ int dstr_notch_apply_host(int n, double s, double eps, const double* x, double* 
 }
 
 int dstr_set_row_filter(dstr_ctx* ctx, int kind) {
-    if (!ctx || kind < 0 || kind > 1) return DSTR_E_ARG;
+    if (!ctx || kind < 0 || kind > 2) return DSTR_E_ARG;
     ctx->row_filter = kind;
     return 0;
 }

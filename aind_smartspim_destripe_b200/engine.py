@@ -542,7 +542,8 @@ class DestripeEngine:
         self._ck(self.lib.dstr_set_umma(self.ctx, 1 if enabled else 0), "dstr_set_umma")
 
     def set_row_filter(self, kind: int):
-        """0: register-tiled FMA row filter, 1 (default): mma.sync row filter."""
+        """0: register-tiled FMA row filter, 1 (default): mma.sync row filter (8 rows per block), 2: the same with 4 rows
+        per block (the fallback form)."""
         self._ck(self.lib.dstr_set_row_filter(self.ctx, int(kind)), "dstr_set_row_filter")
 
     def set_overlap(self, enabled: bool):

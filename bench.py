@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.c3 (dual-config) resident timing")
     ap.add_argument("--umma", action="store_true", help="row filter on the tcgen05 kernel (opt-in: measured slower)")
-    ap.add_argument("--row-filter", type=int, default=-1, help="0: FMA row filter, 1: mma.sync row filter (default: engine default)")
+    ap.add_argument("--row-filter", type=int, default=-1, help="0: FMA row filter, 1: mma.sync row filter with 8 rows per block, 2: with 4 rows (default: engine default = 1)")
     ap.add_argument("--e2e-sync", action="store_true", help="wait for every step's result before submitting the next")
     return ap.parse_args()
 

@@ -210,7 +210,8 @@ int dstr_histogram_u16(dstr_ctx* ctx, const uint16_t* in, int Z, uint32_t* hist)
 int dstr_set_umma(dstr_ctx* ctx, int enabled);
 /* Row filter variant when dstr_set_umma is off: 1 (default; environment DSTR_ROW_FILTER) = the even / odd FIRs and the
  * rank-J correction as mma.sync m16n8k16 products on fp16 hi/lo operand pairs, 8 rows per block
- * (csrc/dstr_rows_mma.cuh), 0 = the register-tiled FMA kernel of round 1.  Same operator design, same parity tests. */
+ * (csrc/dstr_rows_mma.cuh), 2 = the same kernel with 4 rows per block (what bands too long for the 8-row form fall back
+ * to), 0 = the register-tiled FMA kernel of round 1.  Same operator design, same parity tests. */
 int dstr_set_row_filter(dstr_ctx* ctx, int kind);
 /* geometry of the tensor-core row filter for a band of width n:
  * info = {eligible, passes, outputs per pass, k chunks, table bytes, shared memory bytes, outputs, padded K}
