@@ -5,14 +5,15 @@
 CUDA library (C-ABI: include/dstr_b200.h).  No CPU fallback exists.
 """
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from . import engine, filtering, synthetic, zarr_destriper  # noqa: F401
 from .filtering import (  # noqa: F401
     filter_planes,
+    filter_streaks,
     filter_stripes,
     flatfield_correction,
     get_foreground_background_mean,
     log_space_fft_filtering,
 )
-from .zarr_destriper import destripe_volume, execute_worker, z_slab  # noqa: F401
+from .zarr_destriper import destripe_volume, execute_worker, release_volume_resources, z_slab  # noqa: F401

@@ -604,7 +604,6 @@ def destripe_zarr(
     decode / encode threads (0 = 8).  With ``world_size`` > 1 (default: ``WORLD_SIZE`` / ``RANK`` of
     a torchrun launch) every rank processes its own Z-slab; there is no collective.
     """
-    import os
     from pathlib import Path
 
     from . import zarr_store as zs
