@@ -440,3 +440,25 @@ def test_destripe_volume_writes_are_cut_on_sink_chunk_boundaries(tmp_path, produ
     ref = fl.filter_planes(vol[8:], "0_0", no_cells, cells, shadow, 2500)
     np.testing.assert_array_equal(arr[0, 0, 8:], ref)
     assert not list((tmp_path / "0").rglob("*.tmp"))
+
+
+def test_debug_fetch_reports_the_dispatch_decision(production_configs):
+    """DSTR_FETCH_STATS slot 4 is the per-plane cells / no_cells choice the device made (filtering.py:459-467), slots 5 / 6
+    the foreground / background means it was made from."""
+    no_cells, cells = production_configs
+    Z, H, W = 4, 256, 320
+    st = S.synthetic_stack(Z, H, W, base_seed=90, cells_every=2)
+    shadow = _shadow(H, W)
+    eng = E.DestripeEngine(H, W, max_planes=Z)
+    eng.set_subchunk(Z)
+    fl.filter_planes(st, "0_0", no_cells, cells, shadow, 2500, engine=eng)
+    stats = eng.debug_fetch(E.FETCH_STATS, 1, Z)
+    seen = set()
+    for z in range(Z):
+        fg, bg, _ = OF.get_foreground_background_mean(st[z].astype(np.float32))
+        expect = bool(fg > bg and fg > 2500)
+        seen.add(expect)
+        assert bool(stats[z][4]) == expect, (z, stats[z][4:7], fg, bg)
+        assert abs(stats[z][5] - fg) <= 1e-3 * max(1.0, abs(fg)) and abs(stats[z][6] - bg) <= 1e-3 * max(1.0, abs(bg))
+    assert seen == {True, False}
+    eng.close()
